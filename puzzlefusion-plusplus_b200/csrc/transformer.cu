@@ -1,0 +1,344 @@
+// Token-level kernels of the denoiser / verifier transformers (fp32 SIMT):
+// NeRF embeddings + token assembly, (Ada)LayerNorm, variable-length multi-head attention,
+// mean-pool, DDPM posterior step.  The contractions around them go through pfpp_gemm_*.
+#include "common.cuh"
+#include "../../include/pfpp.h"
+
+// ---------------------------------------------------------------------------------------------
+// NeRF embedding features (utils/model_utils.py:40-69; denoiser_transformer.py:117-135)
+//   token features  [latent(64) | nerf(xyz) 63 | nerf(scale) 21 | 0-pad]  -> feat_tok [F*L, ld_tok]
+//   param features  [nerf(x) 147 | 0-pad]                                 -> feat_par [F,   ld_par]
+// nerf(v) = [v, sin(v*2^0), cos(v*2^0), ..., sin(v*2^9), cos(v*2^9)] with v a d-vector, i.e. the
+// output is ordered [v(d) | sin(f0 v)(d) | cos(f0 v)(d) | ...].
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float nerf_feature(const float* v, int d, int c) {
+  // c in [0, d*21)
+  if (c < d) return v[c];
+  int r = c - d;
+  int blk = r / d, comp = r - blk * d;
+  float f = (float)(1 << (blk >> 1));
+  float a = fmul(v[comp], f);
+  return (blk & 1) ? cosf(a) : sinf(a);
+}
+
+template <typename OutT>
+__device__ __forceinline__ OutT cvt_out(float v);
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename OutT>
+__global__ void embed_features_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                      const int* __restrict__ frag_slot, const float* __restrict__ latent,
+                                      const float* __restrict__ xyz, int F, int L, int latent_dim,
+                                      OutT* __restrict__ feat_tok, int ld_tok, OutT* __restrict__ feat_par,
+                                      int ld_par) {
+  int row = blockIdx.x;  // 0..F*L-1 : token rows ; F*L..F*L+F-1 : param rows
+  if (row < F * L) {
+    int f = row / L;
+    int slot = frag_slot[f];
+    float p[3] = {xyz[(size_t)row * 3], xyz[(size_t)row * 3 + 1], xyz[(size_t)row * 3 + 2]};
+    float s = scale[slot];
+    OutT* o = feat_tok + (size_t)row * ld_tok;
+    for (int c = threadIdx.x; c < ld_tok; c += blockDim.x) {
+      float v = 0.f;
+      if (c < latent_dim) v = latent[(size_t)row * latent_dim + c];
+      else if (c < latent_dim + 63) v = nerf_feature(p, 3, c - latent_dim);
+      else if (c < latent_dim + 84) v = nerf_feature(&s, 1, c - latent_dim - 63);
+      o[c] = cvt_out<OutT>(v);
+    }
+  } else {
+    int f = row - F * L;
+    int slot = frag_slot[f];
+    float v7[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) v7[i] = x[(size_t)slot * 7 + i];
+    OutT* o = feat_par + (size_t)f * ld_par;
+    for (int c = threadIdx.x; c < ld_par; c += blockDim.x) o[c] = cvt_out<OutT>(c < 147 ? nerf_feature(v7, 7, c) : 0.f);
+  }
+}
+
+extern "C" int pfpp_embed_features(const float* x, const float* scale, const int* frag_slot, const float* latent,
+                                   const float* xyz, int F, int L, int latent_dim, int out_bf16, void* feat_tok,
+                                   int ld_tok, void* feat_par, int ld_par, cudaStream_t stream) {
+  PFPP_CHECK_ARG(x && scale && frag_slot && latent && xyz && feat_tok && feat_par);
+  PFPP_CHECK_ARG(ld_tok >= latent_dim + 84 && ld_par >= 147);
+  if (F == 0) return PFPP_OK;
+  if (out_bf16)
+    embed_features_kernel<__nv_bfloat16><<<F * L + F, 64, 0, stream>>>(x, scale, frag_slot, latent, xyz, F, L, latent_dim,
+                                                                      (__nv_bfloat16*)feat_tok, ld_tok,
+                                                                      (__nv_bfloat16*)feat_par, ld_par);
+  else
+    embed_features_kernel<float><<<F * L + F, 64, 0, stream>>>(x, scale, frag_slot, latent, xyz, F, L, latent_dim,
+                                                              (float*)feat_tok, ld_tok, (float*)feat_par, ld_par);
+  PFPP_RETURN_LAST();
+}
+
+// h[f*L+l] = shape_emb[f*L+l] + (x_emb[f] + ref_emb[ref[slot]]) + pe[slot % P]
+// (denoiser_transformer.py:150-156,173-185; same association order as the reference)
+__global__ void combine_embed_kernel(const float* __restrict__ shape_emb, const float* __restrict__ x_emb,
+                                     const float* __restrict__ ref_emb, const float* __restrict__ pe,
+                                     const int* __restrict__ frag_slot, const unsigned char* __restrict__ ref, int P,
+                                     int L, int C, float* __restrict__ h) {
+  int row = blockIdx.x;
+  int f = row / L;
+  int slot = frag_slot[f];
+  const float* re = ref_emb + (size_t)(ref[slot] ? 1 : 0) * C;
+  const float* pp = pe + (size_t)(slot % P) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float xe = fadd(x_emb[(size_t)f * C + c], re[c]);
+    float d = fadd(xe, shape_emb[(size_t)row * C + c]);
+    h[(size_t)row * C + c] = fadd(d, pp[c]);
+  }
+}
+
+extern "C" int pfpp_combine_embed(const float* shape_emb, const float* x_emb, const float* ref_emb, const float* pe,
+                                  const int* frag_slot, const unsigned char* ref, int F, int P, int L, int C, float* h,
+                                  cudaStream_t stream) {
+  PFPP_CHECK_ARG(shape_emb && x_emb && ref_emb && pe && frag_slot && ref && h);
+  if (F == 0) return PFPP_OK;
+  combine_embed_kernel<<<F * L, 128, 0, stream>>>(shape_emb, x_emb, ref_emb, pe, frag_slot, ref, P, L, C, h);
+  PFPP_RETURN_LAST();
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm / AdaLayerNorm (attention.py:5-25): one warp per row, eps 1e-5, biased variance.
+//   y = LN(x) * gamma + beta                         (affine)            or
+//   y = LN(x) * (1 + mod[g, 0:C]) + mod[g, C:2C]     (AdaLN, g = row_group[row / rows_per_group])
+// Optionally post-LN residual form y = LN(x + r).
+// ---------------------------------------------------------------------------------------------
+template <int C, typename OutT>
+__global__ void __launch_bounds__(256)
+    layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ mod, const int* __restrict__ row_group,
+                     int rows_per_group, long long rows, OutT* __restrict__ y, float* __restrict__ sum_out) {
+  long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int PER = C / 32;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; i += 4) {
+    float4 t = *reinterpret_cast<const float4*>(x + row * C + (i / 4) * 128 + lane * 4);
+    if (res) {
+      float4 r = *reinterpret_cast<const float4*>(res + row * C + (i / 4) * 128 + lane * 4);
+      t.x += r.x, t.y += r.y, t.z += r.z, t.w += r.w;
+    }
+    v[i] = t.x, v[i + 1] = t.y, v[i + 2] = t.z, v[i + 3] = t.w;
+    s += t.x + t.y + t.z + t.w;
+  }
+  if (sum_out) {
+#pragma unroll
+    for (int i = 0; i < PER; i += 4)
+      *reinterpret_cast<float4*>(sum_out + row * C + (i / 4) * 128 + lane * 4) =
+          make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+  float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    float d = v[i] - mean;
+    q += d * d;
+  }
+  float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+  const float* md = mod ? mod + (size_t)row_group[row / rows_per_group] * 2 * C : nullptr;
+#pragma unroll
+  for (int i = 0; i < PER; i += 4) {
+    int c = (i / 4) * 128 + lane * 4;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float n = (v[i + j] - mean) * rstd;
+      if (md) n = n * (1.0f + md[c + j]) + md[C + c + j];
+      else if (gamma) n = n * gamma[c + j] + beta[c + j];
+      o[j] = n;
+    }
+    OutT* yo = y + row * C + c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) yo[j] = cvt_out<OutT>(o[j]);
+  }
+}
+
+extern "C" int pfpp_layernorm(const float* x, const float* residual, const float* gamma, const float* beta,
+                              const float* mod, const int* row_group, int rows_per_group, long long rows, int C,
+                              int out_bf16, void* y, float* sum_out, cudaStream_t stream) {
+  PFPP_CHECK_ARG(x && y && (C == 512 || C == 256));
+  PFPP_CHECK_ARG(!mod || (row_group && rows_per_group > 0));
+  if (rows == 0) return PFPP_OK;
+  int grid = pfpp_cdiv(rows, 8);
+#define PFPP_LN_CASE(CC, T)                                                                                   \
+  layernorm_kernel<CC, T><<<grid, 256, 0, stream>>>(x, residual, gamma, beta, mod, row_group, rows_per_group, \
+                                                    rows, (T*)y, sum_out)
+  if (C == 512) {
+    if (out_bf16) PFPP_LN_CASE(512, __nv_bfloat16);
+    else PFPP_LN_CASE(512, float);
+  } else {
+    if (out_bf16) PFPP_LN_CASE(256, __nv_bfloat16);
+    else PFPP_LN_CASE(256, float);
+  }
+#undef PFPP_LN_CASE
+  PFPP_RETURN_LAST();
+}
+
+// ---------------------------------------------------------------------------------------------
+// variable-length multi-head attention (fp32 SIMT, flash-style online softmax).
+//   tokens are packed [M, ld] with q/k/v at column offsets; segment s owns rows
+//   [seg_start[s], seg_start[s]+seg_len[s]) and attends fully within itself.  This one kernel is
+//   the denoiser's block-diagonal local attention (segments = fragments, 25 tokens), its global
+//   attention over the valid fragments of an object (<=500 tokens, padded fragments are simply
+//   not in the packed batch, which is what the reference's key mask achieves), and the verifier's
+//   key-padded attention over valid edges.
+//   One thread per query row (q and the output accumulator in registers), K/V tiles of 32 keys
+//   staged in shared memory and read as broadcast LDS.128.
+// ---------------------------------------------------------------------------------------------
+#define ATT_KT 32
+
+template <int D, typename InT, typename OutT>
+__global__ void __launch_bounds__(128)
+    attn_varlen_kernel(const InT* __restrict__ qkv, int ld, int q_off, int k_off, int v_off,
+                       const int* __restrict__ seg_start, const int* __restrict__ seg_len, float scale,
+                       OutT* __restrict__ out, int ldo) {
+  __shared__ __align__(16) float Ks[ATT_KT][D];
+  __shared__ __align__(16) float Vs[ATT_KT][D];
+  const int s = blockIdx.z, h = blockIdx.y;
+  const int len = seg_len[s], st = seg_start[s];
+  const int q0 = blockIdx.x * blockDim.x;
+  if (q0 >= len) return;
+  const int qi = q0 + threadIdx.x;
+  const bool active = qi < len;
+  float q[D], acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    q[d] = active ? (float)qkv[(size_t)(st + qi) * ld + q_off + h * D + d] * scale : 0.f;
+    acc[d] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int kt = 0; kt < len; kt += ATT_KT) {
+    int nk = min(ATT_KT, len - kt);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nk * D; i += blockDim.x) {
+      int r = i / D, d = i - r * D;
+      size_t base = (size_t)(st + kt + r) * ld + h * D + d;
+      Ks[r][d] = (float)qkv[base + k_off];
+      Vs[r][d] = (float)qkv[base + v_off];
+    }
+    __syncthreads();
+    float sc[ATT_KT];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < ATT_KT; ++j) {
+      float a = 0.f;
+      if (j < nk) {
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+          float4 kv = *reinterpret_cast<const float4*>(&Ks[j][d]);
+          a += q[d] * kv.x + q[d + 1] * kv.y + q[d + 2] * kv.z + q[d + 3] * kv.w;
+        }
+        tmax = fmaxf(tmax, a);
+      } else {
+        a = -INFINITY;
+      }
+      sc[j] = a;
+    }
+    float mn = fmaxf(m, tmax);
+    float corr = expf(m - mn);  // exp(-inf) = 0 on the first tile
+    l *= corr;
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] *= corr;
+#pragma unroll
+    for (int j = 0; j < ATT_KT; ++j) {
+      if (j < nk) {
+        float p = expf(sc[j] - mn);
+        l += p;
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+          float4 vv = *reinterpret_cast<const float4*>(&Vs[j][d]);
+          acc[d] += p * vv.x, acc[d + 1] += p * vv.y, acc[d + 2] += p * vv.z, acc[d + 3] += p * vv.w;
+        }
+      }
+    }
+    m = mn;
+  }
+  if (active) {
+    float inv = 1.0f / l;
+    OutT* o = out + (size_t)(st + qi) * ldo + h * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = cvt_out<OutT>(acc[d] * inv);
+  }
+}
+
+extern "C" int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_off, int v_off, const int* seg_start,
+                                     const int* seg_len, int n_segments, int max_len, int heads, int head_dim,
+                                     int io_bf16, void* out, int ldo, cudaStream_t stream) {
+  PFPP_CHECK_ARG(qkv && seg_start && seg_len && out && heads > 0 && (head_dim == 64 || head_dim == 32));
+  if (n_segments == 0 || max_len == 0) return PFPP_OK;
+  int threads = max_len >= 128 ? 128 : ((max_len + 31) / 32) * 32;
+  dim3 grid(pfpp_cdiv(max_len, threads), heads, n_segments);
+  float scale = 1.0f / sqrtf((float)head_dim);
+#define PFPP_ATT_CASE(DD, TI, TO)                                                                            \
+  attn_varlen_kernel<DD, TI, TO><<<grid, threads, 0, stream>>>((const TI*)qkv, ld, q_off, k_off, v_off, \
+                                                               seg_start, seg_len, scale, (TO*)out, ldo)
+  if (head_dim == 64) {
+    if (io_bf16) PFPP_ATT_CASE(64, __nv_bfloat16, __nv_bfloat16);
+    else PFPP_ATT_CASE(64, float, float);
+  } else {
+    if (io_bf16) PFPP_ATT_CASE(32, __nv_bfloat16, __nv_bfloat16);
+    else PFPP_ATT_CASE(32, float, float);
+  }
+#undef PFPP_ATT_CASE
+  PFPP_RETURN_LAST();
+}
+
+// mean over the L tokens of each fragment (denoiser_transformer.py:141-142): [F*L, C] -> [F, C]
+template <typename OutT>
+__global__ void mean_pool_kernel(const float* __restrict__ h, int L, int C, OutT* __restrict__ out) {
+  int f = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += h[((size_t)f * L + l) * C + c];
+    out[(size_t)f * C + c] = cvt_out<OutT>(s / (float)L);
+  }
+}
+
+extern "C" int pfpp_mean_pool(const float* h, int F, int L, int C, int out_bf16, void* out, cudaStream_t stream) {
+  PFPP_CHECK_ARG(h && out);
+  if (F == 0) return PFPP_OK;
+  if (out_bf16) mean_pool_kernel<__nv_bfloat16><<<F, 128, 0, stream>>>(h, L, C, (__nv_bfloat16*)out);
+  else mean_pool_kernel<float><<<F, 128, 0, stream>>>(h, L, C, (float*)out);
+  PFPP_RETURN_LAST();
+}
+
+// ---------------------------------------------------------------------------------------------
+// DDPM posterior step + reference-part clamp (diffusers DDPMScheduler.step, SURVEY App. B.1;
+// auto_aggl.py:149-150).  eps is [F,7] in packed fragment order, x/noise/ref_pose are [slots,7].
+// coef = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_x, sigma}; add_noise = (t > 0).
+// ---------------------------------------------------------------------------------------------
+__global__ void ddpm_step_kernel(const float* __restrict__ eps, int ld_eps, const int* __restrict__ frag_slot,
+                                 const float* __restrict__ coef, const int* __restrict__ frag_coef, int add_noise,
+                                 const float* __restrict__ noise, const unsigned char* __restrict__ ref,
+                                 const float* __restrict__ ref_pose, int F, float* __restrict__ x) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F * 7) return;
+  int f = i / 7, c = i - f * 7;
+  int slot = frag_slot[f];
+  const float* cf = coef + 5 * (frag_coef ? frag_coef[f] : 0);
+  float xv = x[(size_t)slot * 7 + c];
+  float e = eps[(size_t)f * ld_eps + c];
+  float x0 = fdiv(fsub(xv, fmul(cf[0], e)), cf[1]);
+  float prev = fadd(fmul(cf[2], x0), fmul(cf[3], xv));
+  if (add_noise) prev = fadd(prev, fmul(cf[4], noise[(size_t)slot * 7 + c]));
+  if (ref[slot]) prev = ref_pose[(size_t)slot * 7 + c];
+  x[(size_t)slot * 7 + c] = prev;
+}
+
+extern "C" int pfpp_ddpm_step(const float* eps, int ld_eps, const int* frag_slot, const float* coef,
+                              const int* frag_coef, int add_noise, const float* noise, const unsigned char* ref,
+                              const float* ref_pose, int F, float* x, cudaStream_t stream) {
+  PFPP_CHECK_ARG(eps && frag_slot && coef && ref && ref_pose && x && (!add_noise || noise));
+  if (F == 0) return PFPP_OK;
+  ddpm_step_kernel<<<pfpp_cdiv(F * 7, 128), 128, 0, stream>>>(eps, ld_eps, frag_slot, coef, frag_coef, add_noise, noise,
+                                                             ref, ref_pose, F, x);
+  PFPP_RETURN_LAST();
+}

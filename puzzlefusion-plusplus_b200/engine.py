@@ -1,0 +1,242 @@
+"""Host-side orchestration of the denoise-and-verify kernels (one process per GPU).
+
+``Engine`` owns the packed weights, the workspaces and the per-step launch sequence:
+
+  encoder  (per DDPM step; auto_aggl.py:81-92 -> vq_vae.py:52-68 -> pn2.py:57-68)
+      rotate+FPS -> ball query -> gather -> 3x GEMM(+BN+ReLU) -> max   (x3 levels) -> conv6 -> VQ
+  denoiser (denoiser_transformer.py:169-202)
+      NeRF features -> 2 GEMMs -> token assembly -> 6 x [AdaLN, QKV, local attn, out-proj(+res),
+      AdaLN, QKV, global attn, out-proj(+res), LN, GEGLU FF1, FF2(+res)] -> mean-pool -> heads
+  DDPM step + reference clamp (auto_aggl.py:149-150)
+  verifier (auto_aggl.py:156-206; verifier_transformer.py:42-65)
+
+Everything here is launch plumbing: torch is used for device memory and streams only; every op on the
+path is a kernel of libpfpp_sm100.so called through the C ABI.  ``precision`` selects the contraction
+engine: "fp32" = SIMT FFMA GEMMs with fp32 activations (parity mode), "bf16" = tcgen05/TMEM GEMMs with
+bf16 activations and fp32 accumulation / residual stream (fast mode).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EPI_GEGLU, EPI_GELU, EPI_NONE, EPI_RELU, EPI_SILU, call
+from .scheduler import PiecewiseScheduler
+from .weights import DenoiserWeights, EncoderWeights, VerifierWeights
+
+# (npoint, radius, nsample) of the three set-abstraction levels (vqvae/model/modules/pn2.py:16-18)
+SA_CFG = ((256, 0.2, 32), (128, 0.4, 64), (25, 0.8, 64))
+
+
+def _i32(x, device):
+    return torch.as_tensor(np.asarray(x, dtype=np.int32)).to(device)
+
+
+class Engine:
+    def __init__(self, ckpt, num_inference_steps=20, precision="bf16", device="cuda:0", num_layers=6, heads=8,
+                 max_parts=20, latent_points=25, latent_dim=64, verifier_layers=6, sa_cfg=SA_CFG, chunk_frags=32):
+        if not torch.cuda.is_available():
+            raise _lib.PfppError("pfpp-b200 needs a CUDA device (sm_100a); there is no CPU path")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(precision)
+        _lib.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.bf16 = precision == "bf16"
+        self.precision = precision
+        self.act_dtype = torch.bfloat16 if self.bf16 else torch.float32
+        self.kmult = 8 if self.bf16 else 4
+        self.P, self.L, self.latent_dim, self.heads = max_parts, latent_points, latent_dim, heads
+        self.sa_cfg = tuple(sa_cfg)
+        self.chunk = chunk_frags
+        self.sched = PiecewiseScheduler()
+        self.sched.set_timesteps(num_inference_steps)
+        self.T = num_inference_steps
+        self.coef = self.sched.coefficient_table().contiguous().to(self.device)  # [T,5]
+        self.enc = EncoderWeights(ckpt["encoder"], self.device, self.bf16)
+        self.den = DenoiserWeights(ckpt["denoiser"], self.device, self.bf16, num_layers, self.sched.timesteps)
+        self.ver = VerifierWeights(ckpt["verifier"], self.device, verifier_layers) if "verifier" in ckpt else None
+        self.C = self.den.C
+        self._ws = {}
+
+    # ------------------------------------------------------------------ helpers
+    def buf(self, name, shape, dtype):
+        """Named workspace tensor, grown on demand and reused across steps (no per-step allocation)."""
+        n = int(np.prod(shape))
+        t = self._ws.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    def gemm(self, a, lda, lin, out, ldc, M, epi=EPI_NONE, residual=None, ldr=0, out_bf16=None, force_f32=False):
+        """out[M, N'] = epi(a[M,K] @ W^T + b) (+ residual) on the engine selected by the precision mode."""
+        bias = _lib.ptr(lin.b)
+        res = _lib.ptr(residual)
+        if self.bf16 and not force_f32:
+            ob = (out.dtype == torch.bfloat16) if out_bf16 is None else out_bf16
+            call("pfpp_gemm_bf16", a.data_ptr(), lda, lin.w16.data_ptr(), lin.k16, bias, res, ldr, out.data_ptr(), ldc,
+                 int(ob), M, lin.n, lin.k16, epi)
+        else:
+            call("pfpp_gemm_f32", a.data_ptr(), lda, lin.w32.data_ptr(), lin.k32, bias, res, ldr, out.data_ptr(), ldc,
+                 M, lin.n, lin.k32, epi)
+
+    def _pad(self, k):
+        return (k + self.kmult - 1) // self.kmult * self.kmult
+
+    # ------------------------------------------------------------------ encoder
+    def encode(self, part_pcs, frag_slot, x, N, trace=None):
+        """part_pcs [slots,N,3], frag_slot int32 [F], x [slots,7] -> latent [F*L,64] fp32, xyz [F,L,3] fp32."""
+        F = frag_slot.numel()
+        L, act, bf = self.L, self.act_dtype, int(self.bf16)
+        z_e = self.buf("z_e", (F * L, self.latent_dim), torch.float32)
+        xyz_out = self.buf("xyz3", (F, L, 3), torch.float32)
+        latent = self.buf("latent", (F * L, self.latent_dim), torch.float32)
+        Fc = min(self.chunk, F)
+        rot = self.buf("rot", (Fc, N, 3), torch.float32)
+        max_rows = Fc * max(s * ns for s, _, ns in self.sa_cfg)
+        gidx = self.buf("gidx", (max_rows,), torch.int32)
+        chans = [[lin.n for lin in layers] for layers in self.enc.sa]
+        kin = [self._pad(3 + d) for d in (0, chans[0][2], chans[1][2])]
+        X = self.buf("saX", (max(Fc * s * ns * k for (s, _, ns), k in zip(self.sa_cfg, kin)),), act)
+        B1 = self.buf("saB1", (max(Fc * s * ns * c[0] for (s, _, ns), c in zip(self.sa_cfg, chans)),), act)
+        B2 = self.buf("saB2", (max(Fc * s * ns * c[1] for (s, _, ns), c in zip(self.sa_cfg, chans)),), act)
+        B3 = self.buf("saB3", (max(Fc * s * ns * c[2] for (s, _, ns), c in zip(self.sa_cfg, chans)),), act)
+        idx = [self.buf(f"fpsidx{i}", (Fc, s), torch.int32) for i, (s, _, _) in enumerate(self.sa_cfg)]
+        cxyz = [self.buf(f"fpsxyz{i}", (Fc, s, 3), torch.float32) for i, (s, _, _) in enumerate(self.sa_cfg)]
+        feats = [self.buf(f"safeat{i}", (Fc, s, c[2]), act) for i, ((s, _, _), c) in enumerate(zip(self.sa_cfg, chans))]
+        for c0 in range(0, F, Fc):
+            K = min(Fc, F - c0)
+            slot_ptr = frag_slot.data_ptr() + 4 * c0
+            src_xyz, src_n, src_feat, src_d = rot, N, None, 0
+            for li, (S, radius, ns) in enumerate(self.sa_cfg):
+                # the last level's centroids are the encoder's xyz output: write them in place
+                cx = xyz_out[c0:] if li == len(self.sa_cfg) - 1 else cxyz[li]
+                if li == 0:
+                    call("pfpp_rotate_fps", part_pcs.data_ptr(), slot_ptr, K, N, S, x.data_ptr() + 12, 7, rot.data_ptr(),
+                         idx[0].data_ptr(), cx.data_ptr())
+                else:
+                    call("pfpp_fps", src_xyz.data_ptr(), K, src_n, S, None, idx[li].data_ptr(), cx.data_ptr())
+                call("pfpp_ball_query", src_xyz.data_ptr(), cx.data_ptr(), K, src_n, S, float(np.float32(radius ** 2)),
+                     ns, gidx.data_ptr())
+                rows = K * S * ns
+                ld = kin[li]
+                call("pfpp_group_gather", src_xyz.data_ptr(), cx.data_ptr(), _lib.ptr(src_feat), gidx.data_ptr(), K,
+                     src_n, S, ns, src_d, ld, bf, X.data_ptr())
+                l0, l1, l2 = self.enc.sa[li]
+                self.gemm(X, ld, l0, B1, l0.n, rows, EPI_RELU)
+                self.gemm(B1, l0.n, l1, B2, l1.n, rows, EPI_RELU)
+                self.gemm(B2, l1.n, l2, B3, l2.n, rows, EPI_RELU)
+                call("pfpp_group_max", B3.data_ptr(), K * S, ns, l2.n, l2.n, bf, feats[li].data_ptr(), l2.n)
+                if trace is not None:
+                    trace.setdefault(f"sa{li + 1}.fps_idx", []).append(idx[li][:K].clone())
+                    trace.setdefault(f"sa{li + 1}.group_idx", []).append(gidx[:rows].view(K, S, ns).clone())
+                    trace.setdefault(f"sa{li + 1}.feats", []).append(feats[li][:K].float().clone())
+                    if li == 0:
+                        trace.setdefault("rotated", []).append(rot[:K].clone())
+                src_xyz, src_n, src_feat, src_d = cx, S, feats[li], l2.n
+            # conv6 (pn2.py:65): fp32 output for the code search
+            c6 = self.enc.conv6
+            self.gemm(feats[2], c6.k16 if self.bf16 else c6.k32, c6, z_e[c0 * L:], self.latent_dim, K * L, EPI_NONE,
+                      out_bf16=False)
+        codes = self.buf("codes", (F * L * 4,), torch.int32)
+        call("pfpp_vq", z_e.data_ptr(), 0, F * L * (self.latent_dim // 16), self.enc.codebook.data_ptr(),
+             self.enc.codebook.shape[0], latent.data_ptr(), codes.data_ptr())
+        if trace is not None:
+            trace["z_e"] = z_e.clone()
+            trace["codes"] = codes.clone()
+        return latent, xyz_out
+
+    # ------------------------------------------------------------------ denoiser
+    def denoise_eps(self, x, scale, ref, frag_slot, frag_tidx, latent, xyz, seg_local, seg_global, max_global,
+                    trace=None):
+        """One DenoiserTransformer forward on the packed batch -> eps [F, 8] fp32 (cols 0..6 used)."""
+        F = frag_slot.numel()
+        L, C, H, act, bf = self.L, self.C, self.heads, self.act_dtype, int(self.bf16)
+        M = F * L
+        D = C // H
+        w = self.den
+        ld_tok = self._pad(self.latent_dim + 84)
+        ld_par = self._pad(147)
+        feat_tok = self.buf("feat_tok", (M, ld_tok), act)
+        feat_par = self.buf("feat_par", (F, ld_par), act)
+        shape_emb = self.buf("shape_emb", (M, C), torch.float32)
+        x_emb = self.buf("x_emb", (F, C), torch.float32)
+        h = self.buf("h", (M, C), torch.float32)
+        ln = self.buf("ln", (M, C), act)
+        qkv = self.buf("qkv", (M, 3 * C), act)
+        ao = self.buf("ao", (M, C), act)
+        ff = self.buf("ff", (M, 4 * C), act)
+        call("pfpp_embed_features", x.data_ptr(), scale.data_ptr(), frag_slot.data_ptr(), latent.data_ptr(),
+             xyz.data_ptr(), F, L, self.latent_dim, bf, feat_tok.data_ptr(), ld_tok, feat_par.data_ptr(), ld_par)
+        self.gemm(feat_tok, ld_tok, w.shape_embedding, shape_emb, C, M)
+        self.gemm(feat_par, ld_par, w.param_fc, x_emb, C, F)
+        call("pfpp_combine_embed", shape_emb.data_ptr(), x_emb.data_ptr(), w.ref_emb.data_ptr(), w.pe.data_ptr(),
+             frag_slot.data_ptr(), ref.data_ptr(), F, self.P, L, C, h.data_ptr())
+        if trace is not None:
+            trace["data_emb"] = h.clone()
+        loc_start, loc_len = seg_local
+        glo_start, glo_len = seg_global
+        n_obj = glo_start.numel()
+        for li, lw in enumerate(w.layers):
+            for which, (name, segs, nseg, mlen) in enumerate((("self_attn", (loc_start, loc_len), F, L),
+                                                               ("global_attn", (glo_start, glo_len), n_obj, max_global))):
+                mod = w.mod[li * 2 + which]
+                call("pfpp_layernorm", h.data_ptr(), None, None, None, mod.data_ptr(), frag_tidx.data_ptr(), L, M, C, bf,
+                     ln.data_ptr(), None)
+                self.gemm(ln, C, lw[name + ".qkv"], qkv, 3 * C, M)
+                call("pfpp_attention_varlen", qkv.data_ptr(), 3 * C, 0, C, 2 * C, segs[0].data_ptr(), segs[1].data_ptr(),
+                     nseg, mlen, H, D, bf, ao.data_ptr(), C)
+                self.gemm(ao, C, lw[name + ".out"], h, C, M, EPI_NONE, residual=h, ldr=C)
+            call("pfpp_layernorm", h.data_ptr(), None, lw["norm3.w"].data_ptr(), lw["norm3.b"].data_ptr(), None, None, 0, M,
+                 C, bf, ln.data_ptr(), None)
+            self.gemm(ln, C, lw["ff1"], ff, 4 * C, M, EPI_GEGLU)
+            self.gemm(ff, 4 * C, lw["ff2"], h, C, M, EPI_NONE, residual=h, ldr=C)
+            if trace is not None:
+                trace[f"layer{li}"] = h.clone()
+        pooled = self.buf("pooled", (F, C), torch.float32)
+        h0 = self.buf("head0", (F, 2 * C), torch.float32)
+        ht = self.buf("head_t", (F, C // 2), torch.float32)
+        hr = self.buf("head_r", (F, C // 2), torch.float32)
+        eps = self.buf("eps", (F, 8), torch.float32)
+        call("pfpp_mean_pool", h.data_ptr(), F, L, C, 0, pooled.data_ptr())
+        self.gemm(pooled, C, w.head0, h0, 2 * C, F, EPI_SILU, force_f32=True)
+        self.gemm(h0, 2 * C, w.head_t2, ht, C // 2, F, EPI_SILU, force_f32=True)
+        self.gemm(h0[:, C:], 2 * C, w.head_r2, hr, C // 2, F, EPI_SILU, force_f32=True)
+        self.gemm(ht, C // 2, w.head_t4, eps, 8, F, EPI_NONE, force_f32=True)
+        self.gemm(hr, C // 2, w.head_r4, eps[:, 3:], 8, F, EPI_NONE, force_f32=True)
+        return eps
+
+    # ------------------------------------------------------------------ verifier
+    def verifier_logits(self, feat, tok_row, tok_i, tok_j, seg_start, seg_len, max_len, n_rows):
+        """feat [n_rows,7] fp32 dense edge features; packed valid-edge tokens -> logits [n_rows] fp32.
+
+        Always fp32 (the 0.9 acceptance threshold is applied to these logits)."""
+        w = self.ver
+        C, H = w.C, self.heads
+        n = tok_row.numel()
+        h = self.buf("v_h", (n, C), torch.float32)
+        h2 = self.buf("v_h2", (n, C), torch.float32)
+        qkv = self.buf("v_qkv", (n, 3 * C), torch.float32)
+        ao = self.buf("v_ao", (n, C), torch.float32)
+        t1 = self.buf("v_t1", (n, C), torch.float32)
+        ffb = self.buf("v_ff", (n, w.layers[0]["l1"].n), torch.float32)
+        logits = self.buf("v_logits", (n_rows,), torch.float32)
+        logits.zero_()
+        call("pfpp_verifier_embed", feat.data_ptr(), tok_row.data_ptr(), tok_i.data_ptr(), tok_j.data_ptr(), n,
+             w.emb_w.data_ptr(), w.emb_b.data_ptr(), w.pe.data_ptr(), C, h.data_ptr())
+        for lw in w.layers:
+            self.gemm(h, C, lw["qkv"], qkv, 3 * C, n, force_f32=True)
+            call("pfpp_attention_varlen", qkv.data_ptr(), 3 * C, 0, C, 2 * C, seg_start.data_ptr(), seg_len.data_ptr(),
+                 seg_start.numel(), max_len, H, C // H, 0, ao.data_ptr(), C)
+            self.gemm(ao, C, lw["out"], t1, C, n, force_f32=True)
+            # x = LN1(x + attn)      (post-LN TransformerEncoderLayer)
+            call("pfpp_layernorm", h.data_ptr(), t1.data_ptr(), lw["n1w"].data_ptr(), lw["n1b"].data_ptr(), None, None, 0,
+                 n, C, 0, h2.data_ptr(), None)
+            self.gemm(h2, C, lw["l1"], ffb, lw["l1"].n, n, EPI_GELU, force_f32=True)
+            self.gemm(ffb, lw["l1"].n, lw["l2"], t1, C, n, force_f32=True)
+            # x = LN2(x + ff)
+            call("pfpp_layernorm", h2.data_ptr(), t1.data_ptr(), lw["n2w"].data_ptr(), lw["n2b"].data_ptr(), None, None, 0,
+                 n, C, 0, h.data_ptr(), None)
+        call("pfpp_verifier_head", h.data_ptr(), tok_row.data_ptr(), n, w.out_w.data_ptr(), w.out_b.data_ptr(), C,
+             logits.data_ptr())
+        return logits

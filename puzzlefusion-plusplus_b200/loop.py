@@ -1,0 +1,391 @@
+"""The auto-agglomerative denoise -> verify -> merge loop for a BATCH of fractured objects.
+
+Generalises AutoAgglomerative.test_step (puzzlefusion_plusplus/auto_aggl.py:95-319, batch size 1 in the
+reference) to B objects advanced in lock-step on one GPU: the per-DDPM-step work of all valid fragments
+of all active objects is one packed launch sequence (engine.py); the verify stage is one batched
+edge-histogram + verifier pass per outer iteration; the tiny agglomeration-graph state (pivots,
+accumulated init poses, reference flags -- auto_aggl.py:122-131,208-289) stays on the host exactly as in
+the reference, with ONE device->host read per outer iteration instead of one per DDPM step.
+
+Every reference quirk listed in SURVEY.md Appendix C is preserved (un-normalised quaternion for the
+by-area cloud, no re-noising between outer iterations, index-aligned Chamfer in the merge filter, ...).
+Rows of ``x`` that belong to padded or merged-away slots are never read by any valid output (App. C.9,
+C.10) and are left untouched here.
+"""
+import itertools
+
+import networkx as nx
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call
+from .pose_utils import affine, compose_params, compose_params_steps, quat_to_matrix
+
+
+class GlobalTorchNoise:
+    """The reference's RNG protocol (App. C.1): draws from torch's global generator of the device, in
+    the same order and shapes -- randn([B,P,7]) once, then once per step with t > 0, rand(1) per merge."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def initial(self, B, P):
+        return torch.randn((B, P, 7), device=self.device)
+
+    def step(self, B, P):
+        return torch.randn((B, P, 7), device=self.device)
+
+    def fps_start(self, b, M):
+        return int((torch.rand(1, device=self.device) * float(M)).to(torch.int64))
+
+
+class ReplayNoise:
+    """Pre-drawn noise (parity tests: the oracle and this loop consume identical tensors)."""
+
+    def __init__(self, normals, uniforms, device):
+        self.normals = [n.to(device) for n in normals]
+        self.uniforms = list(uniforms)
+
+    def initial(self, B, P):
+        return self.normals.pop(0).reshape(B, P, 7).clone()
+
+    def step(self, B, P):
+        return self.normals.pop(0).reshape(B, P, 7).clone()
+
+    def fps_start(self, b, M):
+        u = self.uniforms.pop(0)
+        return int((u.to(torch.float32) * float(M)).to(torch.int64))
+
+
+class PerObjectNoise:
+    """Batch protocol: object b owns generator seed+b and pre-draws [T,P,7] per outer iteration, so a
+    batch of B objects is bit-identical to B single-object runs."""
+
+    def __init__(self, device, seeds, T):
+        self.device, self.T = device, T
+        self.gens = [torch.Generator(device=device).manual_seed(int(s)) for s in seeds]
+        self.cur = None
+        self.k = 0
+
+    def initial(self, B, P):
+        return torch.cat([torch.randn((1, P, 7), device=self.device, generator=g) for g in self.gens], 0)
+
+    def begin_iteration(self, B, P):
+        self.cur = torch.stack([torch.randn((self.T, P, 7), device=self.device, generator=g) for g in self.gens], 1)
+        self.k = 0
+
+    def step(self, B, P):
+        out = self.cur[self.k]
+        self.k += 1
+        return out
+
+    def fps_start(self, b, M):
+        return int((torch.rand(1, device=self.device, generator=self.gens[b]) * float(M)).to(torch.int64))
+
+
+def _triu_index(P):
+    idx = {}
+    for e, (i, j) in enumerate(itertools.combinations(range(P), 2)):
+        idx[(i, j)] = e
+    return idx
+
+
+class BatchState:
+    """Device + host state of B objects (slots = B*P)."""
+
+    def __init__(self, engine, objects):
+        dev = engine.device
+        self.B, self.P = len(objects), engine.P
+        B, P = self.B, self.P
+        self.N = objects[0]["part_pcs"].shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.part_pcs = torch.stack([o["part_pcs"] for o in objects]).to(**f32).reshape(B * P, self.N, 3).contiguous()
+        self.scale = torch.stack([o["part_scale"].reshape(P) for o in objects]).to(**f32).reshape(B * P).contiguous()
+        self.gt = torch.stack([torch.cat([o["part_trans"], o["part_rots"]], -1) for o in objects]).to(**f32)
+        self.num_parts = [int(o["num_parts"]) for o in objects]
+        self.valid = np.stack([np.asarray(o["part_valids"]) > 0 for o in objects])  # host mirror [B,P]
+        self.ref = np.stack([np.asarray(o["ref_part"]).astype(bool) for o in objects])  # host mirror [B,P]
+        self.scale_host = self.scale.cpu().reshape(B, P).clone()
+        self.pivot = [list(range(n)) for n in self.num_parts]
+        self.node_valid = [[True] * n for n in self.num_parts]
+        self.init_pose = [[None] * n for n in self.num_parts]
+        self.graph = []
+        for n in self.num_parts:
+            g = nx.Graph()
+            g.add_nodes_from(range(n))
+            self.graph.append(g)
+        self.classified = np.zeros((B, P), dtype=bool)
+        self.done = [False] * B
+        self.has_matching = all("part_pcs_by_area" in o for o in objects)
+        if self.has_matching:
+            self._build_matching(objects, dev)
+
+    def _build_matching(self, objects, dev):
+        B, P = self.B, self.P
+        tri = _triu_index(P)
+        self.E_full = P * (P - 1) // 2
+        pts, self.area_base, self.area_cs = [], [], []
+        pair_src, pair_tgt, e_start, e_len, e_row = [], [], [], [], []
+        base, pos = 0, 0
+        for b, o in enumerate(objects):
+            pts.append(o["part_pcs_by_area"].float())
+            n_pcs = np.asarray(o["n_pcs"]).astype(np.int64)
+            cs = np.concatenate([[0], np.cumsum(n_pcs)])
+            self.area_base.append(base)
+            self.area_cs.append(cs)
+            crit = np.asarray(o["critical_pcs_idx"]).astype(np.int64)
+            edges = np.asarray(o["edges"]).reshape(-1, 2)
+            for e in range(edges.shape[0]):
+                idx2, idx1 = int(edges[e, 0]), int(edges[e, 1])
+                corr = np.asarray(o["correspondences"][e]).reshape(-1, 2)
+                src = base + cs[idx1] + crit[cs[idx1] + corr[:, 0]]
+                tgt = base + cs[idx2] + crit[cs[idx2] + corr[:, 1]]
+                pair_src.append(src)
+                pair_tgt.append(tgt)
+                e_start.append(pos)
+                e_len.append(len(src))
+                e_row.append(b * self.E_full + tri[(idx1, idx2)])
+                pos += len(src)
+            base += pts[-1].shape[0]
+        self.by_area = torch.cat(pts, 0).to(dev).contiguous()
+        self.by_area_T = torch.empty_like(self.by_area)
+        i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32).reshape(-1)).to(dev)  # noqa: E731
+        self.pair_src = i32(np.concatenate(pair_src) if pair_src else [])
+        self.pair_tgt = i32(np.concatenate(pair_tgt) if pair_tgt else [])
+        self.e_start, self.e_len, self.e_row = i32(e_start), i32(e_len), i32(e_row)
+        self.n_edges = len(e_start)
+        self.max_pairs = max(e_len) if e_len else 0
+        self.tri_list = list(itertools.combinations(range(P), 2))
+
+
+def _seg_tensors(engine, frag_counts):
+    """local (per fragment) and global (per object) attention segments over the packed tokens."""
+    L, dev = engine.L, engine.device
+    F = int(sum(frag_counts))
+    loc_start = torch.arange(F, dtype=torch.int32, device=dev) * L
+    loc_len = torch.full((F,), L, dtype=torch.int32, device=dev)
+    starts = np.concatenate([[0], np.cumsum(frag_counts)[:-1]]) * L
+    glo_start = torch.as_tensor(starts.astype(np.int32)).to(dev)
+    glo_len = torch.as_tensor((np.asarray(frag_counts) * L).astype(np.int32)).to(dev)
+    return (loc_start, loc_len), (glo_start, glo_len), int(max(frag_counts)) * L
+
+
+def run_batch(engine, objects, max_iters, threshold=0.9, noise=None, merge=True, record=None, trajectory=True):
+    """Run the full loop on a list of per-object dicts (no batch dim).
+
+    Returns dict(x [B,P,7], pred_trans [B,P,3], pred_rots [B,P,4], trajectory list per object
+    ([T_total, n_nodes, 7]), iters [B])."""
+    dev, P, T = engine.device, engine.P, engine.T
+    st = BatchState(engine, objects)
+    B, N = st.B, st.N
+    noise = noise or GlobalTorchNoise(dev)
+    x = noise.initial(B, P).to(torch.float32)
+    ref_mask = torch.as_tensor(st.ref).to(dev)
+    ref_pose = torch.zeros_like(st.gt)
+    ref_pose[ref_mask] = st.gt[ref_mask]
+    x[ref_mask] = ref_pose[ref_mask]
+    x = x.reshape(B * P, 7).contiguous()
+    ref_pose = ref_pose.reshape(B * P, 7).contiguous()
+    ref_dev = ref_mask.reshape(B * P).to(torch.uint8).contiguous()
+    x_hist = torch.empty(max_iters * T, B * P, 7, device=dev)
+    traj = [[] for _ in range(B)]
+    iters = [0] * B
+    timesteps = [int(t) for t in engine.sched.timesteps]
+
+    for it in range(max_iters):
+        active = [b for b in range(B) if not st.done[b]]
+        if not active:
+            break
+        slots, counts = [], []
+        for b in active:
+            s = [b * P + p for p in range(P) if st.valid[b, p]]
+            slots += s
+            counts.append(len(s))
+        frag_slot = torch.as_tensor(np.asarray(slots, dtype=np.int32)).to(dev)
+        F = len(slots)
+        frag_tidx = torch.zeros(F, dtype=torch.int32, device=dev)
+        seg_local, seg_global, max_global = _seg_tensors(engine, counts)
+        if hasattr(noise, "begin_iteration"):
+            noise.begin_iteration(B, P)
+        for si, t in enumerate(timesteps):
+            frag_tidx.fill_(si)
+            latent, xyz = engine.encode(st.part_pcs, frag_slot, x, N)
+            eps = engine.denoise_eps(x, st.scale, ref_dev, frag_slot, frag_tidx, latent, xyz, seg_local, seg_global,
+                                     max_global)
+            nz = noise.step(B, P).reshape(B * P, 7).contiguous() if t > 0 else x
+            call("pfpp_ddpm_step", eps.data_ptr(), 8, frag_slot.data_ptr(), engine.coef.data_ptr() + 20 * si, None, 1,
+                 nz.data_ptr(), ref_dev.data_ptr(), ref_pose.data_ptr(), F, x.data_ptr())
+            x_hist[it * T + si].copy_(x)
+            if record is not None:
+                record.append({"t": t, "eps": eps[:, :7].clone(), "x": x.clone(), "frag_slot": frag_slot.clone()})
+        for b in active:
+            iters[b] += 1
+        x_host = x.cpu().reshape(B, P, 7)  # the one D2H read of this outer iteration
+        xh = x_hist[it * T:(it + 1) * T].cpu().reshape(T, B, P, 7)
+        if trajectory:
+            for b in active:
+                traj[b].append(compose_params_steps(xh[:, b], st.pivot[b], st.init_pose[b]))
+        if it + 1 == max_iters:
+            break
+        _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshold, noise, merge, record)
+
+    x_host = x.cpu().reshape(B, P, 7)
+    pred_t = torch.zeros(B, P, 3)
+    pred_r = torch.zeros(B, P, 4)
+    for b in range(B):
+        tr, qr = compose_params(x_host[b], st.pivot[b], st.init_pose[b])
+        pred_t[b, :st.num_parts[b]] = tr
+        pred_r[b, :st.num_parts[b]] = qr
+    return {"x": x_host, "pred_trans": pred_t, "pred_rots": pred_r,
+            "trajectory": [torch.cat(t) if t else torch.zeros(0) for t in traj], "iters": iters,
+            "pivots": st.pivot, "ref_part": torch.as_tensor(st.ref), "part_valids": torch.as_tensor(st.valid)}
+
+
+def _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshold, noise, merge, record):
+    """auto_aggl.py:156-289 for all active objects."""
+    dev, P, B, N = engine.device, st.P, st.B, st.N
+    i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32).reshape(-1)).to(dev)  # noqa: E731
+    # ---- pose the by-area cloud with the (un-normalised) pivot poses: node_merge_utils.py:16-41
+    seg_s, seg_l, seg_p = [], [], []
+    for b in active:
+        cs, base = st.area_cs[b], st.area_base[b]
+        for i in range(st.num_parts[b]):
+            seg_s.append(base + cs[i])
+            seg_l.append(cs[i + 1] - cs[i])
+            seg_p.append(b * P + st.pivot[b][i])
+    seg_s, seg_l, seg_p = i32(seg_s), i32(seg_l), i32(seg_p)
+    call("pfpp_pose_apply", st.by_area.data_ptr(), seg_s.data_ptr(), seg_l.data_ptr(), seg_p.data_ptr(), x.data_ptr(),
+         None, 0, seg_s.numel(), st.by_area_T.data_ptr())
+    # ---- edge histograms + verifier
+    n_rows = B * st.E_full
+    feat = engine.buf("edge_feat", (n_rows, 7), torch.float32)
+    call("pfpp_edge_features", st.by_area_T.data_ptr(), st.pair_src.data_ptr(), st.pair_tgt.data_ptr(),
+         st.e_start.data_ptr(), st.e_len.data_ptr(), st.e_row.data_ptr(), st.n_edges, max(st.max_pairs, 1), n_rows,
+         feat.data_ptr())
+    tok_row, tok_i, tok_j, seg_start, seg_len = [], [], [], [], []
+    for b in active:
+        seg_start.append(len(tok_row))
+        n = st.num_parts[b]
+        for e, (i, j) in enumerate(st.tri_list):
+            if i < n and j < n:
+                tok_row.append(b * st.E_full + e)
+                tok_i.append(i)
+                tok_j.append(j)
+        seg_len.append(len(tok_row) - seg_start[-1])
+    tok_row, tok_i, tok_j, seg_start_d, seg_len_d = i32(tok_row), i32(tok_i), i32(tok_j), i32(seg_start), i32(seg_len)
+    logits = engine.verifier_logits(feat, tok_row, tok_i, tok_j, seg_start_d, seg_len_d, max(seg_len), n_rows)
+    logits_h = logits.cpu().reshape(B, st.E_full)  # D2H (syncs)
+    if record is not None:
+        record.append({"verify": True, "edge_features": feat.clone().reshape(B, st.E_full, 7), "logits": logits_h.clone()})
+    pred = torch.sigmoid(logits_h) > threshold  # auto_aggl.py:204-205 (edge validity applied below)
+    # reference_gt_and_rots = x.clone() (auto_aggl.py:222) for active objects
+    ref_pose.copy_(x)
+
+    # ---- posed fragment clouds for merging: node_merge_utils.py:43-53 (normalised quaternion)
+    posed = None
+    for b in active:
+        n = st.num_parts[b]
+        ref_idx = [p for p in range(P) if st.ref[b, p]]
+        st.classified[b, ref_idx] = True
+        larger = st.valid[b] & (st.scale_host[b].numpy() > 0.05)
+        accepted = [(i, j) for e, (i, j) in enumerate(st.tri_list)
+                    if i < n and j < n and bool(pred[b, e])]
+        new_ref = []
+        for (i, j) in accepted:
+            i_ref, j_ref = i in ref_idx, j in ref_idx
+            if i_ref == j_ref:
+                continue
+            new_ref.append(j if i_ref else i)
+        for r in new_ref:
+            st.ref[b, r] = True
+        ref_now = [p for p in range(P) if st.ref[b, p]]
+        merge_list = []
+        for (i, j) in accepted:
+            if i in ref_now or j in ref_now:
+                continue
+            if st.ref[b, st.pivot[b][i]] or st.ref[b, st.pivot[b][j]]:
+                continue
+            merge_list.append((i, j))
+        if bool((st.classified[b] == larger).all()):
+            st.done[b] = True
+            continue
+        if merge and merge_list:
+            if posed is None:
+                posed = _posed_fragments(engine, st, x)
+            _merge_components(engine, st, b, merge_list, posed, x_host[b], noise)
+        # the reference re-tests with the `larger_parts` computed before the merge (auto_aggl.py:288)
+        if bool((st.classified[b] == larger).all()):
+            st.done[b] = True
+    ref_dev.copy_(torch.as_tensor(st.ref).reshape(B * P).to(torch.uint8).to(dev))
+
+
+def _posed_fragments(engine, st, x):
+    dev, P, B, N = engine.device, st.P, st.B, st.N
+    nseg = B * P
+    seg_s = torch.arange(nseg, dtype=torch.int32, device=dev) * N
+    seg_l = torch.full((nseg,), N, dtype=torch.int32, device=dev)
+    seg_p = torch.arange(nseg, dtype=torch.int32, device=dev)
+    out = engine.buf("posed", (nseg, N, 3), torch.float32)
+    call("pfpp_pose_apply", st.part_pcs.data_ptr(), seg_s.data_ptr(), seg_l.data_ptr(), seg_p.data_ptr(), x.data_ptr(),
+         st.scale.data_ptr(), 1, nseg, out.data_ptr())
+    return out
+
+
+def _merge_components(engine, st, b, merge_list, posed, xb, noise):
+    """auto_aggl.py:234-286 for object b."""
+    dev, P, N = engine.device, st.P, st.N
+    G = st.graph[b]
+    G.add_edges_from(merge_list)
+    trans, rots = xb[:, :3], xb[:, 3:]
+    rot_m = quat_to_matrix(rots)
+    for comp in list(nx.connected_components(G)):
+        comp = list(comp)
+        if sum(st.node_valid[b][c] for c in comp) <= 1:
+            continue
+        pivot = max(comp, key=lambda c: st.scale_host[b, c])
+        members = [c for c in comp if st.node_valid[b][c]]
+        merged = torch.cat([posed[b * P + c] for c in members], 0)
+        centroid = merged.mean(dim=0)
+        merged = (merged - centroid).contiguous()
+        centroid_h = centroid.cpu()
+        for c in comp:
+            pv = st.pivot[b][c]
+            m = affine(rot_m[pv], trans[pv] - centroid_h)
+            st.init_pose[b][c] = m if st.init_pose[b][c] is None else m @ st.init_pose[b][c]
+        cs, base = st.area_cs[b], st.area_base[b]
+        for c in comp:
+            st.by_area[base + cs[c]:base + cs[c + 1]] = st.by_area_T[base + cs[c]:base + cs[c + 1]] - centroid
+        for c in comp:
+            st.pivot[b][c] = pivot
+        ds = _remove_intersect_and_fps(engine, merged, len(members), N, noise, b)
+        mscale = ds.abs().max()
+        st.scale[b * P + pivot] = mscale
+        st.scale_host[b, pivot] = mscale.cpu()
+        st.part_pcs[b * P + pivot] = ds / mscale
+        for c in comp:
+            st.valid[b, c] = False
+            st.node_valid[b][c] = c == pivot
+        st.valid[b, pivot] = True
+        st.classified[b, comp] = True
+
+
+def _remove_intersect_and_fps(engine, merged, n_clouds, N, noise, b):
+    """node_merge_utils.py:159-222 on device: normals + pairwise filter kernel, compaction, FPS to N."""
+    dev = engine.device
+    keep = torch.empty(n_clouds * N, dtype=torch.uint8, device=dev)
+    normals = torch.empty(n_clouds * N, 3, dtype=torch.float32, device=dev)
+    call("pfpp_merge_filter", merged.data_ptr(), n_clouds, N, 20, float(np.float32(0.001)), keep.data_ptr(),
+         normals.data_ptr())
+    pts = merged[keep.bool()].contiguous()
+    M = pts.shape[0]
+    ratio = torch.tensor(N / M, dtype=torch.float32)
+    n_out = int(torch.ceil(torch.tensor(float(M), dtype=torch.float32) * ratio))
+    start = noise.fps_start(b, M)
+    # [cloud_start, cloud_len, n_samples, start, out_start] -- kept alive until after the launch
+    meta = torch.as_tensor(np.asarray([0, M, n_out, start, 0], dtype=np.int32)).to(dev)
+    out_idx = torch.empty(n_out, dtype=torch.int32, device=dev)
+    dist = torch.empty(M, dtype=torch.float32, device=dev)
+    mp = meta.data_ptr()
+    call("pfpp_fps_ragged", pts.data_ptr(), mp, mp + 4, mp + 8, mp + 12, 1, dist.data_ptr(), mp + 16, out_idx.data_ptr())
+    return pts[out_idx.long()][:N]

@@ -1,0 +1,131 @@
+"""Weight packing: reference ``state_dict``s -> flat device buffers in the layouts the kernels read.
+
+Input keys/shapes are exactly the reference checkpoints' (test.py:24-38
+prefix-stripped).  Packing does, once per checkpoint:
+  * BatchNorm (eval) folded into the 1x1-conv weight/bias in float64 (utils/pn2_utils.py:209-212);
+  * K dimension zero-padded to the GEMM engines' alignment (4 fp32 / 8 bf16 elements);
+  * to_q/to_k/to_v concatenated into one [3C, C] projection (attention.py:46-72 via diffusers);
+  * GEGLU projection rows interleaved (value_j, gate_j) so the activation fuses into the epilogue;
+  * the two output heads' first layers concatenated;
+  * AdaLN modulation rows Linear(SiLU(Embedding[t])) tabulated for the scheduler's T timesteps
+    (attention.py:22-24; they depend only on (layer, t));
+  * bf16 copies for the tcgen05 path.
+"""
+import torch
+
+from . import _lib
+from ._lib import EPI_NONE
+
+
+def _pad_k(w, mult):
+    n, k = w.shape
+    kp = (k + mult - 1) // mult * mult
+    if kp == k:
+        return w.contiguous()
+    out = w.new_zeros(n, kp)
+    out[:, :k] = w
+    return out
+
+
+class Linear:
+    """One packed projection: fp32 [N, K4] (+ optional bf16 [N, K8]) and fp32 bias."""
+
+    def __init__(self, w, b, device, bf16):
+        w = w.detach().to(torch.float32)
+        self.n, self.k = w.shape
+        self.w32 = _pad_k(w, 4).to(device)
+        self.k32 = self.w32.shape[1]
+        self.b = None if b is None else b.detach().to(torch.float32).contiguous().to(device)
+        self.w16 = None
+        if bf16:
+            self.w16 = _pad_k(w, 8).to(device).to(torch.bfloat16).contiguous()
+            self.k16 = self.w16.shape[1]
+
+
+def fold_bn(sd, prefix, i):
+    w = sd[f"{prefix}.mlp_convs.{i}.weight"].double().flatten(1)
+    b = sd[f"{prefix}.mlp_convs.{i}.bias"].double()
+    g = sd[f"{prefix}.mlp_bns.{i}.weight"].double()
+    beta = sd[f"{prefix}.mlp_bns.{i}.bias"].double()
+    mean = sd[f"{prefix}.mlp_bns.{i}.running_mean"].double()
+    var = sd[f"{prefix}.mlp_bns.{i}.running_var"].double()
+    s = g / torch.sqrt(var + 1e-5)
+    return (w * s[:, None]).float(), ((b - mean) * s + beta).float()
+
+
+class EncoderWeights:
+    def __init__(self, sd, device, bf16):
+        self.sa = []
+        for li in range(3):
+            layers = []
+            for i in range(3):
+                w, b = fold_bn(sd, f"pn2.sa{li + 1}", i)
+                layers.append(Linear(w, b, device, bf16))
+            self.sa.append(layers)
+        self.conv6 = Linear(sd["pn2.conv6.weight"].flatten(1), sd["pn2.conv6.bias"], device, bf16)
+        self.codebook = sd["vector_quantization.embedding.weight"].detach().float().contiguous().to(device)
+
+
+class DenoiserWeights:
+    def __init__(self, sd, device, bf16, num_layers, timesteps):
+        C = sd["param_fc.weight"].shape[0]
+        self.C = C
+        self.layers = []
+        ts = torch.as_tensor(timesteps, dtype=torch.long)
+        mods = []
+        for i in range(num_layers):
+            p = f"transformer_layers.{i}"
+            L = {}
+            for a in ("self_attn", "global_attn"):
+                wqkv = torch.cat([sd[f"{p}.{a}.to_q.weight"], sd[f"{p}.{a}.to_k.weight"], sd[f"{p}.{a}.to_v.weight"]], 0)
+                L[a + ".qkv"] = Linear(wqkv, None, device, bf16)
+                L[a + ".out"] = Linear(sd[f"{p}.{a}.to_out.0.weight"], sd[f"{p}.{a}.to_out.0.bias"], device, bf16)
+            w1, b1 = sd[f"{p}.ff.net.0.proj.weight"], sd[f"{p}.ff.net.0.proj.bias"]
+            half = w1.shape[0] // 2
+            wi = torch.stack([w1[:half], w1[half:]], 1).reshape(2 * half, -1)
+            bi = torch.stack([b1[:half], b1[half:]], 1).reshape(2 * half)
+            L["ff1"] = Linear(wi, bi, device, bf16)
+            L["ff2"] = Linear(sd[f"{p}.ff.net.2.weight"], sd[f"{p}.ff.net.2.bias"], device, bf16)
+            L["norm3.w"] = sd[f"{p}.norm3.weight"].detach().float().contiguous().to(device)
+            L["norm3.b"] = sd[f"{p}.norm3.bias"].detach().float().contiguous().to(device)
+            self.layers.append(L)
+            for n in ("norm1", "norm2"):
+                emb = sd[f"{p}.{n}.emb.weight"][ts].float().to(device)
+                a = torch.nn.functional.silu(emb).contiguous()
+                lin = Linear(sd[f"{p}.{n}.linear.weight"], sd[f"{p}.{n}.linear.bias"], device, False)
+                out = torch.empty(len(ts), 2 * C, device=device, dtype=torch.float32)
+                _lib.call("pfpp_gemm_f32", a.data_ptr(), C, lin.w32.data_ptr(), lin.k32, lin.b.data_ptr(), None, 0,
+                          out.data_ptr(), 2 * C, len(ts), 2 * C, C, EPI_NONE)
+                mods.append(out)
+        # mod[(layer*2 + which)] : [T, 2C] -- rows selected per fragment by the current step index
+        self.mod = torch.stack(mods, 0).contiguous()
+        self.shape_embedding = Linear(sd["shape_embedding.weight"], sd["shape_embedding.bias"], device, bf16)
+        self.param_fc = Linear(sd["param_fc.weight"], sd["param_fc.bias"], device, bf16)
+        self.ref_emb = sd["ref_part_emb.weight"].detach().float().contiguous().to(device)
+        self.pe = sd["pos_encoding.pe"][0].detach().float().contiguous().to(device)  # [P, C]
+        self.head0 = Linear(torch.cat([sd["mlp_out_trans.0.weight"], sd["mlp_out_rot.0.weight"]], 0),
+                            torch.cat([sd["mlp_out_trans.0.bias"], sd["mlp_out_rot.0.bias"]], 0), device, False)
+        self.head_t2 = Linear(sd["mlp_out_trans.2.weight"], sd["mlp_out_trans.2.bias"], device, False)
+        self.head_r2 = Linear(sd["mlp_out_rot.2.weight"], sd["mlp_out_rot.2.bias"], device, False)
+        self.head_t4 = Linear(sd["mlp_out_trans.4.weight"], sd["mlp_out_trans.4.bias"], device, False)
+        self.head_r4 = Linear(sd["mlp_out_rot.4.weight"], sd["mlp_out_rot.4.bias"], device, False)
+
+
+class VerifierWeights:
+    def __init__(self, sd, device, num_layers):
+        self.C = sd["edge_feature_emb.weight"].shape[0]
+        f = lambda k: sd[k].detach().float().contiguous().to(device)  # noqa: E731
+        self.emb_w, self.emb_b = f("edge_feature_emb.weight"), f("edge_feature_emb.bias")
+        self.pe = sd["edge_indices_pe.pe"][0].detach().float().contiguous().to(device)
+        self.out_w, self.out_b = f("mlp_out.weight").reshape(-1), f("mlp_out.bias")
+        self.layers = []
+        for i in range(num_layers):
+            p = f"transformer_encoder.layers.{i}"
+            self.layers.append({
+                "qkv": Linear(sd[f"{p}.self_attn.in_proj_weight"], sd[f"{p}.self_attn.in_proj_bias"], device, False),
+                "out": Linear(sd[f"{p}.self_attn.out_proj.weight"], sd[f"{p}.self_attn.out_proj.bias"], device, False),
+                "l1": Linear(sd[f"{p}.linear1.weight"], sd[f"{p}.linear1.bias"], device, False),
+                "l2": Linear(sd[f"{p}.linear2.weight"], sd[f"{p}.linear2.bias"], device, False),
+                "n1w": f(f"{p}.norm1.weight"), "n1b": f(f"{p}.norm1.bias"),
+                "n2w": f(f"{p}.norm2.weight"), "n2b": f(f"{p}.norm2.bias"),
+            })

@@ -1,0 +1,184 @@
+"""GPU parity tests of the composed path (encoder, denoiser, verifier, full loop) against the oracle
+and the committed reference goldens.  Tolerances are stated per test; "fp32" = parity mode (SIMT fp32
+contractions), "bf16" = fast mode (tcgen05 bf16 contractions, fp32 accumulation)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import denoiser as od
+from oracle import encoder as oe
+from oracle import loop as ol
+from oracle import verifier as ov
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def engines(ckpt):
+    from puzzlefusion_plusplus_b200.engine import Engine
+    cache = {}
+
+    def get(precision, steps):
+        key = (precision, steps)
+        if key not in cache:
+            cache[key] = Engine(ckpt, num_inference_steps=steps, precision=precision, device=DEV)
+        return cache[key]
+    return get
+
+
+def _encode_golden(engine):
+    g = load_golden("encoder")
+    K = 3
+    pcs = g["pcs"].to(DEV).contiguous()
+    x = torch.cat([torch.zeros(K, 3), g["quat"]], -1).to(DEV).contiguous()
+    slot = torch.arange(K, dtype=torch.int32, device=DEV)
+    trace = {}
+    latent, xyz = engine.encode(pcs, slot, x, 1000, trace=trace)
+    torch.cuda.synchronize()
+    return g, latent.cpu().reshape(K, 25, 64), xyz.cpu().clone(), trace
+
+
+def test_encoder_fp32_vs_reference_golden(engines, ckpt):
+    """fp32 mode vs the reference's VQVAE.encode: FPS / ball-query indices bit-exact, z_q within 2e-4
+    wherever the VQ code agrees (>= 97 % of the 16-d chunks; argmin near-ties may flip, App. C.4)."""
+    g, latent, xyz, tr = _encode_golden(engines("fp32", 20))
+    assert torch.equal(tr["rotated"][0].cpu(), g["rotated"])
+    assert torch.equal(tr["sa1.fps_idx"][0].cpu().long(), g["sa1_fps_idx"])
+    assert (tr["sa1.group_idx"][0].cpu().long() == g["sa1_group_idx"]).float().mean() >= 0.999
+    assert torch.equal(xyz, g["xyz"])
+    otr = {}
+    oe.vqvae_encode(ckpt["encoder"], g["rotated"], trace=otr)
+    for lvl in ("sa1", "sa2", "sa3"):
+        a, b = tr[f"{lvl}.feats"][0].cpu(), otr[f"{lvl}.feats"]
+        assert (a - b).abs().max() <= 2e-4 * max(1.0, b.abs().max()), lvl
+    z_e = tr["z_e"].cpu().reshape(3, 25, 64)
+    assert (z_e - otr["z_e"]).abs().max() <= 5e-4
+    same = tr["codes"].cpu().long().reshape(3, 100) == otr["codes"]
+    assert same.float().mean() >= 0.97, same.float().mean()
+    diff = (latent - g["z_q"]).reshape(3, 100, 16).abs().amax(-1)
+    assert diff[same].max() <= 2e-4
+
+
+def test_encoder_bf16_close(engines, ckpt):
+    """fast mode: geometry indices still bit-exact (fp32), features within bf16 tolerance (5e-2 of scale)."""
+    g, latent, xyz, tr = _encode_golden(engines("bf16", 20))
+    assert torch.equal(tr["sa1.fps_idx"][0].cpu().long(), g["sa1_fps_idx"])
+    assert torch.equal(xyz, g["xyz"])
+    otr = {}
+    oe.vqvae_encode(ckpt["encoder"], g["rotated"], trace=otr)
+    z_e = tr["z_e"].cpu().reshape(3, 25, 64)
+    rel = (z_e - otr["z_e"]).abs().max() / otr["z_e"].abs().max()
+    assert rel <= 5e-2, rel
+
+
+def _denoise_golden(engine):
+    g = load_golden("denoiser")
+    B, P, L = 2, 20, 25
+    valid = g["part_valids"].reshape(-1) > 0
+    slots = torch.nonzero(valid).reshape(-1).to(torch.int32)
+    F = slots.numel()
+    ts = [int(t) for t in engine.sched.timesteps]
+    tidx = torch.tensor([ts.index(int(g["timesteps"][int(s) // P])) for s in slots], dtype=torch.int32)
+    latent = g["latent"].reshape(B * P, L, 64)[valid].reshape(F * L, 64).to(DEV).contiguous()
+    xyz = g["xyz"].reshape(B * P, L, 3)[valid].to(DEV).contiguous()
+    x = g["x"].reshape(B * P, 7).to(DEV).contiguous()
+    scale = g["scale"].reshape(B * P).to(DEV).contiguous()
+    ref = g["ref_part"].reshape(B * P).to(torch.uint8).to(DEV)
+    counts = [int(valid[:P].sum()), int(valid[P:].sum())]
+    from puzzlefusion_plusplus_b200.loop import _seg_tensors
+    seg_local, seg_global, max_global = _seg_tensors(engine, counts)
+    trace = {}
+    eps = engine.denoise_eps(x, scale, ref, slots.to(DEV), tidx.to(DEV), latent, xyz, seg_local, seg_global, max_global,
+                             trace=trace)
+    torch.cuda.synchronize()
+    return g, eps.cpu()[:, :7], g["eps"].reshape(B * P, 7)[valid], trace
+
+
+def test_denoiser_fp32_vs_reference_golden(engines, ckpt):
+    """fp32 mode vs the reference's DenoiserTransformer.forward (B=2, second object 13 valid parts,
+    different timesteps per object): |eps - eps_ref| <= 1e-4 (pose-parameter units)."""
+    g, eps, ref, tr = _denoise_golden(engines("fp32", 100))
+    assert (eps - ref).abs().max() <= 1e-4, (eps - ref).abs().max()
+
+
+def test_denoiser_bf16_close(engines):
+    """fast mode: bf16 operands through 6 layers; stated tolerance 3e-2 absolute on eps (|eps| ~ 0.05-0.3)."""
+    g, eps, ref, tr = _denoise_golden(engines("bf16", 100))
+    assert (eps - ref).abs().max() <= 3e-2, (eps - ref).abs().max()
+
+
+def test_verifier_vs_reference_golden(engines):
+    """fp32 verifier logits vs the reference VerifierTransformer on valid edges: <= 2e-4."""
+    e = engines("fp32", 20)
+    g = load_golden("verifier")
+    B, E = 2, 190
+    feat = g["edge_features"].reshape(B * E, 7).to(DEV).contiguous()
+    mask = g["edge_valids"]
+    tok_row, tok_i, tok_j, seg_start, seg_len = [], [], [], [], []
+    for b in range(B):
+        seg_start.append(len(tok_row))
+        for k in range(E):
+            if mask[b, k]:
+                tok_row.append(b * E + k)
+                tok_i.append(int(g["edge_indices"][b, k, 0]))
+                tok_j.append(int(g["edge_indices"][b, k, 1]))
+        seg_len.append(len(tok_row) - seg_start[-1])
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32)).to(DEV)  # noqa: E731
+    a, b_, c, d, f = t(tok_row), t(tok_i), t(tok_j), t(seg_start), t(seg_len)
+    logits = e.verifier_logits(feat, a, b_, c, d, f, max(seg_len), B * E).cpu().reshape(B, E)
+    ref = g["logits"][..., 0]
+    assert (logits - ref)[mask].abs().max() <= 2e-4, (logits - ref)[mask].abs().max()
+
+
+def test_loop_config1_vs_reference_golden(engines):
+    """BASELINE config 1 (2 fragments x 256 pts, 10 DDPM steps, denoiser only), fp32 mode, the
+    reference's own noise replayed: final poses of the valid fragments within 1e-4 of the reference."""
+    from puzzlefusion_plusplus_b200 import synthetic
+    from puzzlefusion_plusplus_b200.loop import ReplayNoise, run_batch
+    g = load_golden("loop_config1")
+    obj = synthetic.make_object(123, num_parts=2, n_points=256)
+    noise = ReplayNoise([g["noise"][i] for i in range(10)], [], DEV)
+    rec = []
+    out = run_batch(engines("fp32", 10), [obj], max_iters=1, noise=noise, record=rec)
+    err = (out["x"][0, :2] - g["x_final"][0, :2]).abs().max().item()
+    step_err = [(r["x"].cpu()[:2] - g["trajectory"][i, :2]).abs().max().item() for i, r in enumerate(rec)]
+    assert err <= 1e-4, (err, step_err)
+
+
+def test_loop_full_vs_oracle(engines, ckpt):
+    """denoise + verify + merge (8 fragments, 4 steps, 4 outer iterations) vs the oracle loop with the
+    same noise: identical agglomeration decisions (pivots, reference promotion), poses within 2e-3."""
+    from puzzlefusion_plusplus_b200 import synthetic
+    from puzzlefusion_plusplus_b200.loop import ReplayNoise, run_batch
+    for seed in (321, 323):
+        obj = synthetic.make_object(seed, num_parts=8)
+        gen = torch.Generator().manual_seed(seed)
+        normals = [torch.randn(1, 20, 7, generator=gen) for _ in range(1 + 16)]
+        uniforms = [torch.rand(1, generator=gen) for _ in range(8)]
+        res = ol.run_object(ckpt["encoder"], ckpt["denoiser"], ckpt["verifier"], obj, 4, 4,
+                            rng=ol.ReplayRNG(normals, uniforms))
+        # the oracle draws noise only for t > 0 (3 of 4 steps): build the same consumption order
+        out = run_batch(engines("fp32", 4), [obj], max_iters=4, noise=ReplayNoise(normals, uniforms, DEV))
+        piv_ref = [res["graph"].nodes[i]["pivot"] for i in range(8)]
+        assert out["pivots"][0] == piv_ref, (out["pivots"][0], piv_ref)
+        assert torch.equal(out["ref_part"][0], res["ref_part"])
+        assert out["iters"][0] == res["iters"]
+        valid = res["part_valids"] > 0
+        assert (out["x"][0][valid] - res["x"][valid]).abs().max() <= 2e-3
+        assert (out["pred_trans"][0, :8] - res["pred_trans"][:8]).abs().max() <= 2e-3
+
+
+def test_batch_equals_singles(engines):
+    """B objects in one packed batch == B single-object runs (per-object noise protocol), bit for bit."""
+    from puzzlefusion_plusplus_b200 import synthetic
+    from puzzlefusion_plusplus_b200.loop import PerObjectNoise, run_batch
+    e = engines("bf16", 4)
+    objs = [synthetic.make_object(500 + i, num_parts=n) for i, n in enumerate((5, 9, 3))]
+    seeds = [11, 12, 13]
+    batch = run_batch(e, objs, max_iters=2, noise=PerObjectNoise(DEV, seeds, 4), trajectory=False)
+    for i, o in enumerate(objs):
+        single = run_batch(e, [o], max_iters=2, noise=PerObjectNoise(DEV, seeds[i:i + 1], 4), trajectory=False)
+        n = o["num_parts"]
+        assert torch.equal(single["x"][0, :n], batch["x"][i, :n])
