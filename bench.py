@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- objects/sec of the denoise-and-verify hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+A "step" is one pass of the hot path over one batch of synthetic objects of BASELINE config 2:
+20 fragments x 1000 points, 100 DDPM steps (encoder + denoiser + DDPM update each), then one
+verifier pass (pose by-area clouds, edge histograms, verifier transformer, accept decisions).
+``--batch`` objects are advanced in lock-step per GPU (default 32); objects/sec = batch*K*N / time.
+
+  value : device-timed (CUDA events on the launch stream), inputs already resident in HBM
+  e2e   : the same batch through the public call (run_batch on HOST tensors): H2D of every input
+          and D2H of the predicted poses inside the timed region
+  roofline : the tcgen05 GEMM kernel, algorithmic FLOPs / CUDA-event time of its launches, measured
+          live in the timed region, against MEASURED_PEAKS.json (sustained bf16)
+  cpu_baseline : the oracle (CPU port of the reference path) on the host cores, bounded sample
+
+Multi-GPU (torchrun, one rank per GPU): objects are independent, so ranks run disjoint batches with
+no data-path collective; one NCCL all_gather of the per-object metric block ends every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "objects/sec (full auto-aggl loop, 20 frags, 100 DDPM steps) @1/2/4/8 B200"
+UNIT = "objects/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=32, help="objects in flight per GPU")
+    ap.add_argument("--frags", type=int, default=20)
+    ap.add_argument("--points", type=int, default=1000)
+    ap.add_argument("--ddpm-steps", type=int, default=100)
+    ap.add_argument("--cpu-sample-steps", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=32)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"config2: {a.frags} frags x {a.points} pts, {a.ddpm_steps} DDPM steps, 1 denoise pass + 1 verifier pass; "
+            f"{a.batch} objects in flight per GPU")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_objects_per_sec(a, sample_steps):
+    """Times `sample_steps` DDPM steps (encoder + denoiser + scheduler) and one verify pass of ONE
+    config-2 object with the oracle on all host cores; extrapolates to ddpm_steps per object."""
+    from oracle import denoiser as od
+    from oracle import encoder as oe
+    from oracle import verifier as ov
+    from puzzlefusion_plusplus_b200 import synthetic
+    torch.set_num_threads(os.cpu_count())
+    ck = synthetic.make_checkpoints(0)
+    obj = synthetic.make_object(1000, num_parts=a.frags, n_points=a.points)
+    sched = od.make_scheduler(a.ddpm_steps)
+    g = torch.Generator().manual_seed(0)
+    P = 20
+    x = torch.randn(P, 7, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for t in sched.timesteps[:sample_steps]:
+            latent, xyz = oe.extract_features(ck["encoder"], obj["part_pcs"][None], obj["part_valids"][None], x[None])
+            eps = od.denoiser_forward(ck["denoiser"], x[None], t.reshape(1), latent, xyz, obj["part_valids"][None],
+                                      obj["part_scale"][None], obj["ref_part"][None])[0]
+            x = sched.step(eps, t, x, noise=torch.randn(P, 7, generator=g)).prev_sample
+        t_step = (time.perf_counter() - t0) / sample_steps
+        t1 = time.perf_counter()
+        pts = ov.final_pose_pts_dynamic(obj["part_pcs_by_area"], obj["n_pcs"], x[:, :3], x[:, 3:], a.frags,
+                                        list(range(a.frags)))
+        feats, eidx = ov.edge_features(pts, obj["n_pcs"], obj["n_critical_pcs"], obj["critical_pcs_idx"], obj["edges"],
+                                       obj["correspondences"], P)
+        ov.verifier_forward(ck["verifier"], feats[None], eidx[None], ov.edge_mask(a.frags, P)[None])
+        t_verify = time.perf_counter() - t1
+    per_object = a.ddpm_steps * t_step + t_verify
+    return 1.0 / per_object, t_step, t_verify
+
+
+def run_reference(a, rank):
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(a.warmup):
+        cpu_objects_per_sec(a, 1)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        v, t_step, t_verify = cpu_objects_per_sec(a, a.cpu_sample_steps)
+        vals.append(v)
+    ms = (time.perf_counter() - t0) * 1e3 / max(a.steps, 1)
+    v = float(np.median(vals))
+    sample = (f"{a.cpu_sample_steps} of {a.ddpm_steps} DDPM steps + 1 verifier pass of one object, extrapolated to "
+              f"{a.ddpm_steps} steps; {t_step * 1e3:.0f} ms/DDPM step, {t_verify * 1e3:.0f} ms/verify")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.stop = [], False
+        self.index = index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# per-launch event timing of the dominant kernel (tcgen05 GEMM)
+# ------------------------------------------------------------------------------------------------
+class GemmProbe:
+    """Wraps _lib.call: CUDA events around every pfpp_gemm_bf16 (or pfpp_gemm_f32) launch in the timed region."""
+
+    def __init__(self, lib, name):
+        self.lib, self.name = lib, name
+        self.events, self.flops = [], 0.0
+        self.orig = lib.call
+        self.enabled = False
+
+    def install(self, modules):
+        probe = self
+
+        def call(name, *args):
+            if probe.enabled and name == probe.name:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                probe.orig(name, *args)
+                e1.record()
+                probe.events.append((e0, e1))
+                if name == "pfpp_gemm_bf16":
+                    M, N, K = args[10], args[11], args[12]
+                else:
+                    M, N, K = args[9], args[10], args[11]
+                probe.flops += 2.0 * M * N * K
+            else:
+                probe.orig(name, *args)
+        self.lib.call = call
+        for m in modules:
+            m.call = call
+
+    def result(self):
+        ms = sum(a.elapsed_time(b) for a, b in self.events)
+        return self.flops, ms, len(self.events)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+
+    import torch.distributed as dist
+    from puzzlefusion_plusplus_b200 import _lib, engine as engine_mod, loop as loop_mod, synthetic, weights as weights_mod
+    from puzzlefusion_plusplus_b200.engine import Engine
+    from puzzlefusion_plusplus_b200.loop import BatchState, PerObjectNoise, run_batch
+    from puzzlefusion_plusplus_b200.metrics import object_metrics
+
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    ck = synthetic.make_checkpoints(0)
+    eng = Engine(ck, num_inference_steps=a.ddpm_steps, precision=a.precision, device=dev, chunk_frags=a.chunk)
+    # distinct objects per rank (weak scaling: per-GPU work fixed)
+    n_unique = min(a.batch, 8)
+    uniq = [synthetic.make_object(2000 + rank * 64 + i, num_parts=a.frags, n_points=a.points) for i in range(n_unique)]
+    objects = [uniq[i % n_unique] for i in range(a.batch)]
+    seeds = [rank * 10007 + i for i in range(a.batch)]
+    gemm_name = "pfpp_gemm_bf16" if a.precision == "bf16" else "pfpp_gemm_f32"
+    probe = GemmProbe(_lib, gemm_name)
+    probe.install([engine_mod, loop_mod, weights_mod])
+
+    def one_step(resident_state=None):
+        noise = PerObjectNoise(dev, seeds, a.ddpm_steps)
+        out = run_batch(eng, objects, max_iters=1, noise=noise, trajectory=False, state=resident_state,
+                        verify_last=True)
+        m = object_metrics(out, objects).to(dev)  # [B,4] per-object metric block
+        if world > 1:
+            gathered = torch.empty(world * m.shape[0], m.shape[1], device=dev)
+            dist.all_gather_into_tensor(gathered, m)
+            m = gathered
+        return m
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(a.warmup):
+        one_step(BatchState(eng, objects))
+    states = [BatchState(eng, objects) for _ in range(a.steps)]
+    barrier()
+    launches0 = _lib.launch_count
+    probe.enabled = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for k in range(a.steps):
+            metrics = one_step(states[k])
+        e1.record()
+        barrier()
+    probe.enabled = False
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - launches0
+    t = torch.tensor([elapsed_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = a.batch * world * a.steps / (elapsed_ms * 1e-3)
+
+    # ---- end-to-end: host tensors in, poses out ----
+    barrier()
+    w0 = time.perf_counter()
+    for k in range(a.steps):
+        one_step(None)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = a.batch * world * a.steps / float(t.item())
+    o = objects[0]
+    h2d = a.batch * sum(int(v.numel() * v.element_size()) for k, v in o.items() if torch.is_tensor(v) and k in (
+        "part_pcs", "part_scale", "part_trans", "part_rots", "part_pcs_by_area"))
+    d2h = a.batch * (20 * 7 * 4 * 2 + 190 * 4)
+
+    flops, gemm_ms, n_gemm = probe.result()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if a.precision == "bf16":
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured (sustained bf16, MEASURED_PEAKS.json)" if peaks else "fallback"
+    else:
+        peak = 72.0  # fp32 FFMA nominal: 148 SM x 128 lanes x 2 x 1.9 GHz (no measured fp32 peak is provided)
+        peak_src = "nominal fp32 FFMA"
+    achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "precision_mode": a.precision,
+                   "l2": "per-step working set (activations of one fragment chunk) exceeds L2; inputs differ per step"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "roofline": {"bound": "tensor", "kernel": gemm_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "launches": n_gemm, "kernel_ms_per_step": gemm_ms / a.steps,
+                     "share_of_step": gemm_ms / elapsed_ms if elapsed_ms else None},
+    }
+    if rank == 0:
+        if not a.no_cpu_baseline and world == 1:
+            v, t_step, t_verify = cpu_objects_per_sec(a, a.cpu_sample_steps)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "sample": f"{a.cpu_sample_steps} of {a.ddpm_steps} DDPM steps + 1 verifier pass of one object, "
+                          f"extrapolated; {t_step * 1e3:.0f} ms/DDPM step"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

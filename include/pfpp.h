@@ -166,6 +166,10 @@ int pfpp_verifier_head(const float* h, const int* tok_row, int n_tokens, const f
 int pfpp_merge_filter(const float* pcs, int n_clouds, int n_points, int knn, float threshold, unsigned char* keep,
                       float* normals, cudaStream_t stream);
 
+/* chamferdist / pytorch3d knn_points(K=1) squared distances for the evaluation metrics
+ * (denoiser/evaluation/evaluator.py:108,137): out[b,i] = min_j |a[b,i] - b[b,j]|^2. */
+int pfpp_nn_sqdist(const float* a, const float* b, int batches, int N, int M, float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

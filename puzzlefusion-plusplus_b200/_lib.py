@@ -43,6 +43,7 @@ SIGNATURES = {
     "pfpp_verifier_embed": [_P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P],
     "pfpp_verifier_head": [_P, _P, _I, _P, _P, _I, _P, _P],
     "pfpp_merge_filter": [_P, _I, _I, _I, _F, _P, _P, _P],
+    "pfpp_nn_sqdist": [_P, _P, _I, _I, _I, _P, _P],
 }
 
 _lib = None

@@ -131,3 +131,46 @@ extern "C" int pfpp_verifier_head(const float* h, const int* tok_row, int n_toke
   verifier_head_kernel<<<pfpp_cdiv(n_tokens, 4), 128, 0, stream>>>(h, tok_row, n_tokens, w, b, C, logits);
   PFPP_RETURN_LAST();
 }
+
+// ---------------------------------------------------------------------------------------------
+// Brute-force nearest-neighbour squared distance between batched clouds (chamferdist / pytorch3d
+// knn_points K=1 semantics): out[b,i] = min_j |a[b,i]-b[b,j]|^2.
+// Used by the evaluation metrics (evaluator.py:108,137).  The target cloud streams through shared
+// memory in 1024-point tiles; each thread owns one query point.  ((dx^2+dy^2)+dz^2, ops rounded
+// individually, so the result is bit-identical to the oracle).
+// ---------------------------------------------------------------------------------------------
+#define NN_TILE 1024
+
+__global__ void __launch_bounds__(256)
+    nn_sqdist_kernel(const float* __restrict__ a, const float* __restrict__ b, int N, int M, float* __restrict__ out) {
+  __shared__ float bx[NN_TILE], by[NN_TILE], bz[NN_TILE];
+  const int batch = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* pa = a + ((size_t)batch * N + (i < N ? i : 0)) * 3;
+  const float ax = pa[0], ay = pa[1], az = pa[2];
+  const float* pb = b + (size_t)batch * M * 3;
+  float best = INFINITY;
+  for (int t0 = 0; t0 < M; t0 += NN_TILE) {
+    int nt = min(NN_TILE, M - t0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+      bx[j] = pb[(size_t)(t0 + j) * 3], by[j] = pb[(size_t)(t0 + j) * 3 + 1], bz[j] = pb[(size_t)(t0 + j) * 3 + 2];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < nt; ++j) {
+      float dx = fsub(ax, bx[j]), dy = fsub(ay, by[j]), dz = fsub(az, bz[j]);
+      best = fminf(best, fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));
+    }
+  }
+  if (i < N) out[(size_t)batch * N + i] = best;
+}
+
+extern "C" int pfpp_nn_sqdist(const float* a, const float* b, int batches, int N, int M, float* out,
+                              cudaStream_t stream) {
+  PFPP_CHECK_ARG(a && b && out && N > 0 && M > 0 && batches >= 0);
+  if (batches == 0) return PFPP_OK;
+  dim3 grid(pfpp_cdiv(N, 256), batches);
+  nn_sqdist_kernel<<<grid, 256, 0, stream>>>(a, b, N, M, out);
+  PFPP_RETURN_LAST();
+}

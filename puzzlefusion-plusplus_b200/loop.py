@@ -171,13 +171,15 @@ def _seg_tensors(engine, frag_counts):
     return (loc_start, loc_len), (glo_start, glo_len), int(max(frag_counts)) * L
 
 
-def run_batch(engine, objects, max_iters, threshold=0.9, noise=None, merge=True, record=None, trajectory=True):
+def run_batch(engine, objects, max_iters, threshold=0.9, noise=None, merge=True, record=None, trajectory=True,
+              state=None, verify_last=False):
     """Run the full loop on a list of per-object dicts (no batch dim).
 
-    Returns dict(x [B,P,7], pred_trans [B,P,3], pred_rots [B,P,4], trajectory list per object
-    ([T_total, n_nodes, 7]), iters [B])."""
+    ``state`` may carry a pre-built BatchState (inputs already resident in HBM; a BatchState is
+    consumed by the run).  Returns dict(x [B,P,7], pred_trans [B,P,3], pred_rots [B,P,4], trajectory
+    list per object ([T_total, n_nodes, 7]), iters [B])."""
     dev, P, T = engine.device, engine.P, engine.T
-    st = BatchState(engine, objects)
+    st = state if state is not None else BatchState(engine, objects)
     B, N = st.B, st.N
     noise = noise or GlobalTorchNoise(dev)
     x = noise.initial(B, P).to(torch.float32)
@@ -226,9 +228,13 @@ def run_batch(engine, objects, max_iters, threshold=0.9, noise=None, merge=True,
         if trajectory:
             for b in active:
                 traj[b].append(compose_params_steps(xh[:, b], st.pivot[b], st.init_pose[b]))
+        if it + 1 == max_iters and not verify_last:
+            break
+        # verify_last: BASELINE config 2 = one denoise pass + one verifier pass (no merge, no second pass)
+        _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshold, noise,
+                          merge and it + 1 < max_iters, record)
         if it + 1 == max_iters:
             break
-        _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshold, noise, merge, record)
 
     x_host = x.cpu().reshape(B, P, 7)
     pred_t = torch.zeros(B, P, 3)

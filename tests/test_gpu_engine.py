@@ -182,3 +182,20 @@ def test_batch_equals_singles(engines):
         single = run_batch(e, [o], max_iters=2, noise=PerObjectNoise(DEV, seeds[i:i + 1], 4), trajectory=False)
         n = o["num_parts"]
         assert torch.equal(single["x"][0, :n], batch["x"][i, :n])
+
+
+def test_metrics_block_vs_reference_golden():
+    """device metrics (pose apply + NN kernels) vs the reference's evaluator outputs (goldens):
+    part_acc exact, the rest within 1e-4 relative."""
+    from puzzlefusion_plusplus_b200 import synthetic
+    from puzzlefusion_plusplus_b200.metrics import metrics_block
+    for seed in (321, 323):
+        g = load_golden(f"loop_full_{seed}")
+        obj = synthetic.make_object(seed, num_parts=8)
+        d = lambda t: t[None].to(DEV)  # noqa: E731
+        pts = d(obj["part_pcs"] * obj["part_scale"].unsqueeze(-1))
+        m = metrics_block(pts, d(g["final_trans"]), d(g["final_rots"]), d(obj["part_trans"]), d(obj["part_rots"]),
+                          d(obj["part_valids"])).cpu()[0]
+        ref = torch.stack([g["acc"][0], g["rmse_r"][0], g["rmse_t"][0], g["cd"][0]])
+        assert m[0] == ref[0]
+        assert torch.allclose(m[1:], ref[1:], rtol=1e-4), (m, ref)
