@@ -130,6 +130,13 @@ int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_off, int v_o
                           const int* seg_len, int n_segments, int max_len, int heads, int head_dim, int io_bf16,
                           void* out, int ldo, cudaStream_t stream);
 
+/* The denoiser's global attention (attention.py:84: diffusers Attention with the key mask) on the
+ * tensor cores: bf16 qkv [M, 3C] (q | k | v, head h at columns h*64), segments of <= 512 tokens,
+ * head_dim 64; S = QK^T and O = PV run as tcgen05.mma with fp32 accumulators in TMEM, operands by TMA.
+ * out is bf16 [M, C]. */
+int pfpp_attention_tc(const void* qkv, long long M, int ld, int C, const int* seg_start, const int* seg_len,
+                      int n_segments, int max_len, int heads, void* out, int ldo, cudaStream_t stream);
+
 /* mean over L (denoiser_transformer.py:141-142). */
 int pfpp_mean_pool(const float* h, int F, int L, int C, int out_bf16, void* out, cudaStream_t stream);
 

@@ -56,6 +56,7 @@ class Engine:
         self.den = DenoiserWeights(ckpt["denoiser"], self.device, self.bf16, num_layers, self.sched.timesteps)
         self.ver = VerifierWeights(ckpt["verifier"], self.device, verifier_layers) if "verifier" in ckpt else None
         self.C = self.den.C
+        self.tc_attention = True  # tcgen05 global attention in bf16 mode (segments <= 512 tokens)
         self._ws = {}
 
     # ------------------------------------------------------------------ helpers
@@ -184,8 +185,12 @@ class Engine:
                 call("pfpp_layernorm", h.data_ptr(), None, None, None, mod.data_ptr(), frag_tidx.data_ptr(), L, M, C, bf,
                      ln.data_ptr(), None)
                 self.gemm(ln, C, lw[name + ".qkv"], qkv, 3 * C, M)
-                call("pfpp_attention_varlen", qkv.data_ptr(), 3 * C, 0, C, 2 * C, segs[0].data_ptr(), segs[1].data_ptr(),
-                     nseg, mlen, H, D, bf, ao.data_ptr(), C)
+                if self.bf16 and which == 1 and mlen <= 512 and D == 64 and self.tc_attention:
+                    call("pfpp_attention_tc", qkv.data_ptr(), M, 3 * C, C, segs[0].data_ptr(), segs[1].data_ptr(), nseg,
+                         mlen, H, ao.data_ptr(), C)
+                else:
+                    call("pfpp_attention_varlen", qkv.data_ptr(), 3 * C, 0, C, 2 * C, segs[0].data_ptr(),
+                         segs[1].data_ptr(), nseg, mlen, H, D, bf, ao.data_ptr(), C)
                 self.gemm(ao, C, lw[name + ".out"], h, C, M, EPI_NONE, residual=h, ldr=C)
             call("pfpp_layernorm", h.data_ptr(), None, lw["norm3.w"].data_ptr(), lw["norm3.b"].data_ptr(), None, None, 0, M,
                  C, bf, ln.data_ptr(), None)

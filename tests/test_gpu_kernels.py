@@ -349,3 +349,28 @@ def test_merge_filter_matches_oracle(lib):
     assert (cos > 0.99).float().mean().item() >= 0.98, (cos > 0.99).float().mean().item()
     agree = (keep.cpu().bool().reshape(3, 1000) == keep_ref).float().mean().item()
     assert agree >= 0.995, agree
+
+
+@pytest.mark.parametrize("lens", [[500], [500, 325, 50, 128, 129], [25, 512, 257]])
+def test_attention_tcgen05(lib, lens):
+    """tcgen05 global attention (bf16 operands, fp32 softmax/accumulation) vs torch SDPA on the same
+    bf16-rounded q/k/v: tolerance 2e-2 absolute (bf16 P and bf16 output rounding)."""
+    H, D = 8, 64
+    C = H * D
+    M = sum(lens)
+    g = torch.Generator().manual_seed(M)
+    qkv = torch.randn(M, 3 * C, generator=g).to(torch.bfloat16)
+    out = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    ds, dl = torch.as_tensor(starts).to(DEV), torch.as_tensor(np.asarray(lens, dtype=np.int32)).to(DEV)
+    dq = qkv.to(DEV)
+    lib.call("pfpp_attention_tc", dq.data_ptr(), M, 3 * C, C, ds.data_ptr(), dl.data_ptr(), len(lens), max(lens), H,
+             out.data_ptr(), C)
+    torch.cuda.synchronize()
+    o = out.cpu().float()
+    f = qkv.float()
+    for s, n in zip(starts, lens):
+        q, k, v = [t.view(n, H, D).transpose(0, 1) for t in f[s:s + n].chunk(3, -1)]
+        ref = torch.nn.functional.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1).reshape(n, C)
+        err = (o[s:s + n] - ref).abs().max().item()
+        assert err <= 2e-2, (n, err)
