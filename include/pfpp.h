@@ -86,6 +86,16 @@ int pfpp_group_max(const void* in, long long G, int ns, int C, int ld_in, int is
 int pfpp_vq(const void* z, int z_is_bf16, long long n_chunks, const float* codebook, int n_codes, float* out,
             int* codes, cudaStream_t stream);
 
+/* sample_and_group's gather + PointNetSetAbstraction's 3 x relu(bn(conv1x1)) + max over nsample
+ * (utils/pn2_utils.py:139-148,209-214) fused in one tcgen05 kernel; activations stay in shared
+ * memory / TMEM.  level in {1,2,3} selects (nsample, D, C1, C2, C3) = (32,0,64,64,128),
+ * (64,128,128,128,256), (64,256,256,256,512).  feats [K,N,D] bf16; w0 [C1, ldw0] bf16 with columns
+ * ordered [feats(D) | dx dy dz | 0-pad to a multiple of 16]; w1 [C2,C1], w2 [C3,C2] bf16 (BN folded);
+ * out [K*S, C3] bf16. */
+int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K, int N,
+                  int S, const void* w0, int ldw0, const float* b0, const void* w1, const float* b1, const void* w2,
+                  const float* b2, void* out, cudaStream_t stream);
+
 /* ---- contractions ---------------------------------------------------------------------- */
 
 /* C[M,N'] = epi(A[M,K] W[N,K]^T + bias) (+ residual); fp32 SIMT (parity mode).  Replaces

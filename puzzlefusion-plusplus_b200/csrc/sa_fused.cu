@@ -1,0 +1,382 @@
+// Fused PointNet++ set-abstraction MLP on the 5th-gen tensor cores:
+//   grouping gather -> 3 x (1x1 conv + folded BN + ReLU) -> max over nsample      in ONE kernel
+// (utils/pn2_utils.py:139-148 and :209-214).  Activations never leave the SM: the gathered rows and
+// the two hidden layers live in shared memory as bf16 UMMA operand tiles, accumulators in TMEM.
+//
+// One CTA owns 128 grouped rows (4 groups of 32 samples, or 2 groups of 64).
+//   layers 0,1  D[rows x C] = X[rows x K] . W^T   rows on the M axis; the epilogue thread owns one row,
+//               adds the bias, applies ReLU and writes the bf16 row into the next layer's K-major
+//               SWIZZLE_128B operand tile (16-byte stores).
+//   layer 2     D[C x rows] = W[C x K] . X^T      channels on the M axis (128 per MMA block); the
+//               epilogue thread owns one channel, so the max over a group's nsample rows is a plain
+//               register reduction over TMEM columns; bias + ReLU commute with the max.
+// CTA = 5 warps: warps 0-3 gather / issue MMAs (lane 0 of warp 1) / run the epilogues, warp 4 is the TMA
+// weight producer.  Weight tiles [128 x 64] stream through a ring (full/empty mbarriers) that runs ahead across
+// layer boundaries; X tiles are written by the CTA's own threads (generic proxy) and published to the
+// tensor core with fence.proxy.async.
+//
+// Column order of layer 0 is [feats(D) | dx dy dz | 0-pad] (the host permutes W0 accordingly) so that
+// feature rows are gathered with aligned 16-byte loads/stores.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "../../include/pfpp.h"
+
+namespace {
+
+constexpr uint32_t SF_TILE = 128 * 64 * 2;  // one [128 x 64] bf16 operand panel / weight stage = 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+// K-major SWIZZLE_128B tile: [rows x 64] bf16, 128 B per row, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// D=f32, A=B=bf16, both K-major, M=128, N=128
+constexpr uint32_t SF_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// byte offset of element (row, k) inside a K-major SW128 operand made of 64-wide panels
+__device__ __forceinline__ uint32_t xoff(int row, int k) {
+  return (uint32_t)(k >> 6) * SF_TILE + (uint32_t)row * 128u + (uint32_t)((((k & 63) >> 3) ^ (row & 7)) << 4) +
+         (uint32_t)((k & 7) << 1);
+}
+
+struct SaParams {
+  const float* xyz;        // [K, N, 3] source points of this level
+  const float* new_xyz;    // [K, S, 3] centroids
+  const __nv_bfloat16* feats;  // [K, N, D] previous level features (nullptr when D == 0)
+  const int* gidx;         // [K, S, NS]
+  const float* b0;
+  const float* b1;
+  const float* b2;
+  __nv_bfloat16* out;      // [K*S, C3]
+  int N, S;
+  long long groups;        // K * S
+};
+
+template <int NS, int D, int C1, int C2, int C3, int STAGES>
+struct SaCfg {
+  static constexpr int K0 = ((D + 3 + 15) / 16) * 16;       // layer-0 K, multiple of UMMA_K
+  static constexpr int P0 = (K0 + 63) / 64;                 // panels of X0
+  static constexpr int P1 = (C1 + 63) / 64, P2 = (C2 + 63) / 64;
+  static constexpr int NB1 = (C1 + 127) / 128, NB2 = (C2 + 127) / 128, MB3 = C3 / 128;
+  static constexpr int XA_PANELS = (P0 > P2 ? P0 : P2);     // X0 and X2 share a buffer
+  static constexpr uint32_t OFF_XA = 0;
+  static constexpr uint32_t OFF_XB = XA_PANELS * SF_TILE;   // X1
+  static constexpr uint32_t OFF_W = OFF_XB + P1 * SF_TILE;
+  static constexpr uint32_t OFF_BAR = OFF_W + STAGES * SF_TILE;
+  static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = (C3 > 256 || C1 > 256 || C2 > 256) ? 512 : ((C3 > 128 || C1 > 128 || C2 > 128) ? 256 : 128);
+  static constexpr int G = 128 / NS;                        // groups per CTA
+};
+
+template <int NS, int D, int C1, int C2, int C3, int STAGES>
+__global__ void __launch_bounds__(160)
+    sa_fused_kernel(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
+                    const __grid_constant__ CUtensorMap map_w2, const SaParams p) {
+  using Cfg = SaCfg<NS, D, C1, C2, C3, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_full = base + Cfg::OFF_BAR;             // [STAGES]
+  const uint32_t bar_empty = bar_full + 8 * STAGES;          // [STAGES]
+  const uint32_t bar_acc = bar_empty + 8 * STAGES;           // accumulator of the current layer complete
+  const uint32_t tmem_slot = bar_acc + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long g0 = (long long)blockIdx.x * Cfg::G;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *reinterpret_cast<uint32_t*>(bp + Cfg::OFF_BAR + 16 * STAGES + 8);
+
+  // ---------------- weight producer: one elected thread, runs ahead over all three layers ----------
+  // stage order == consumption order of the MMA issuer below
+  if (warp == 4) {
+    if (lane != 0) return;
+    int it = 0;
+    auto push = [&](const CUtensorMap* m, int kcol, int row) {
+      const int s = it % STAGES;
+      const uint32_t round = it / STAGES;
+      mbar_wait(bar_empty + 8 * s, (round & 1) ^ 1);
+      mbar_expect_tx(bar_full + 8 * s, SF_TILE);
+      tma_load_2d(base + Cfg::OFF_W + s * SF_TILE, m, bar_full + 8 * s, kcol, row);
+      ++it;
+    };
+    for (int nb = 0; nb < Cfg::NB1; ++nb)
+      for (int kp = 0; kp < Cfg::P0; ++kp) push(&map_w0, kp * 64, nb * 128);
+    for (int nb = 0; nb < Cfg::NB2; ++nb)
+      for (int kp = 0; kp < Cfg::P1; ++kp) push(&map_w1, kp * 64, nb * 128);
+    for (int mb = 0; mb < Cfg::MB3; ++mb)
+      for (int kp = 0; kp < Cfg::P2; ++kp) push(&map_w2, kp * 64, mb * 128);
+    return;  // the ring drains on its own; shared memory stays live until the compute warps exit
+  }
+
+  // ---------------- gather: X0[row] = [feats[idx] | xyz[idx]-centroid | 0] (bf16, swizzled) ----------
+  {
+    uint8_t* xa = bp + Cfg::OFF_XA;
+    // zero the tail panel columns that the MMA will read beyond D+3 (K0 is a multiple of 16)
+    for (int r = warp; r < 128; r += 4) {
+      const long long g = g0 + r / NS;
+      const bool valid = g < p.groups;
+      int idx = 0;
+      long long k = 0;
+      if (valid) {
+        idx = p.gidx[g * NS + (r % NS)];
+        k = g / p.S;
+      }
+      if (D > 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.feats + ((size_t)k * p.N + idx) * D);
+        for (int c8 = lane; c8 < D / 8; c8 += 32) {
+          uint4 v = valid ? src[c8] : make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(xa + xoff(r, c8 * 8)) = v;
+        }
+      }
+      // tail: columns D .. K0-1 (xyz offsets then zeros); K0 - D <= 16
+      if (lane < Cfg::K0 - D) {
+        float v = 0.f;
+        if (valid && lane < 3) v = fsub(p.xyz[((size_t)k * p.N + idx) * 3 + lane], p.new_xyz[g * 3 + lane]);
+        *reinterpret_cast<__nv_bfloat16*>(xa + xoff(r, D + lane)) = __float2bfloat16_rn(v);
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+
+  int w_it = 0;  // consumer position in the weight ring (thread 32 only)
+  uint32_t acc_phase = 0;
+
+  // ---------------- layers 0 and 1: rows on M ----------------
+#pragma unroll
+  for (int layer = 0; layer < 2; ++layer) {
+    const int KSTEPS = layer == 0 ? Cfg::K0 / 16 : C1 / 16;
+    const int PANELS = layer == 0 ? Cfg::P0 : Cfg::P1;
+    const int NB = layer == 0 ? Cfg::NB1 : Cfg::NB2;
+    const int COUT = layer == 0 ? C1 : C2;
+    const uint32_t xin = base + (layer == 0 ? Cfg::OFF_XA : Cfg::OFF_XB);
+    uint8_t* xout = bp + (layer == 0 ? Cfg::OFF_XB : Cfg::OFF_XA);
+    const float* bias = layer == 0 ? p.b0 : p.b1;
+    if (threadIdx.x == 32) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int nb = 0; nb < NB; ++nb) {
+        for (int kp = 0; kp < PANELS; ++kp) {
+          const int s = w_it % STAGES;
+          mbar_wait(bar_full + 8 * s, (w_it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = desc_kmajor(xin + kp * SF_TILE), db = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE);
+          const int ks = min(4, KSTEPS - kp * 4);
+          for (int k = 0; k < ks; ++k) umma_bf16(tmem + nb * 128, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
+          umma_commit(bar_empty + 8 * s);
+          ++w_it;
+        }
+      }
+      umma_commit(bar_acc);
+    }
+    __syncwarp();
+    mbar_wait(bar_acc, acc_phase);
+    acc_phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: thread = row; bias + ReLU -> bf16 -> next operand tile
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < COUT / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + c * 32, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float a = fmaxf(__uint_as_float(v[j]) + bias[c * 32 + j], 0.f);
+        float b = fmaxf(__uint_as_float(v[j + 1]) + bias[c * 32 + j + 1], 0.f);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
+        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(xout + xoff(row, c * 32 + i * 8)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+
+  // ---------------- layer 2: channels on M, rows on N; max over each group's columns ----------------
+  if (threadIdx.x == 32) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t xin = base + Cfg::OFF_XA;
+    for (int mb = 0; mb < Cfg::MB3; ++mb) {
+      for (int kp = 0; kp < Cfg::P2; ++kp) {
+        const int s = w_it % STAGES;
+        mbar_wait(bar_full + 8 * s, (w_it / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE), db = desc_kmajor(xin + kp * SF_TILE);
+        const int ks = min(4, C2 / 16 - kp * 4);
+        for (int k = 0; k < ks; ++k) umma_bf16(tmem + mb * 128, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
+        umma_commit(bar_empty + 8 * s);
+        ++w_it;
+      }
+    }
+    umma_commit(bar_acc);
+  }
+  __syncwarp();
+  mbar_wait(bar_acc, acc_phase);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int mb = 0; mb < Cfg::MB3; ++mb) {
+      const int ch = mb * 128 + warp * 32 + lane;
+      const float bias = p.b2[ch];
+#pragma unroll 1
+      for (int g = 0; g < Cfg::G; ++g) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NS / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + mb * 128 + g * NS + c * 32, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        const long long grp = g0 + g;
+        if (grp < p.groups) p.out[grp * C3 + ch] = __float2bfloat16_rn(fmaxf(m + bias, 0.f));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS));
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+int weight_map(CUtensorMap* map, const void* w, int rows, int cols, int ld) {
+  auto fn = encode_fn();
+  if (!fn) return PFPP_EUNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PFPP_OK : PFPP_EINVAL;
+}
+
+template <int NS, int D, int C1, int C2, int C3, int STAGES>
+int launch_sa(const SaParams& p, const void* w0, int ldw0, const void* w1, const void* w2, cudaStream_t stream) {
+  using Cfg = SaCfg<NS, D, C1, C2, C3, STAGES>;
+  CUtensorMap m0, m1, m2;
+  int rc = weight_map(&m0, w0, C1, Cfg::K0, ldw0);
+  if (rc) return rc;
+  rc = weight_map(&m1, w1, C2, C1, C1);
+  if (rc) return rc;
+  rc = weight_map(&m2, w2, C3, C2, C2);
+  if (rc) return rc;
+  auto kern = sa_fused_kernel<NS, D, C1, C2, C3, STAGES>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  const long long tiles = (p.groups + Cfg::G - 1) / Cfg::G;
+  kern<<<(unsigned)tiles, 160, Cfg::SMEM, stream>>>(m0, m1, m2, p);
+  PFPP_RETURN_LAST();
+}
+
+}  // namespace
+
+extern "C" int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K,
+                             int N, int S, const void* w0, int ldw0, const float* b0, const void* w1, const float* b1,
+                             const void* w2, const float* b2, void* out, cudaStream_t stream) {
+  PFPP_CHECK_ARG(xyz && new_xyz && gidx && w0 && w1 && w2 && b0 && b1 && b2 && out && K >= 0 && (ldw0 % 8) == 0);
+  if (K == 0) return PFPP_OK;
+  SaParams p{xyz, new_xyz, (const __nv_bfloat16*)feats, gidx, b0, b1, b2, (__nv_bfloat16*)out, N, S, (long long)K * S};
+  switch (level) {
+    case 1:
+      return launch_sa<32, 0, 64, 64, 128, 2>(p, w0, ldw0, w1, w2, stream);
+    case 2:
+      PFPP_CHECK_ARG(feats);
+      return launch_sa<64, 128, 128, 128, 256, 4>(p, w0, ldw0, w1, w2, stream);
+    case 3:
+      PFPP_CHECK_ARG(feats);
+      return launch_sa<64, 256, 256, 256, 512, 4>(p, w0, ldw0, w1, w2, stream);
+    default:
+      return PFPP_EINVAL;
+  }
+}

@@ -32,6 +32,9 @@ def _i32(x, device):
 
 
 class Engine:
+    # (nsample, D, C1, C2, C3) -> level id understood by pfpp_sa_fused
+    _FUSED_LEVELS = {(32, 0, 64, 64, 128): 1, (64, 128, 128, 128, 256): 2, (64, 256, 256, 256, 512): 3}
+
     def __init__(self, ckpt, num_inference_steps=20, precision="bf16", device="cuda:0", num_layers=6, heads=8,
                  max_parts=20, latent_points=25, latent_dim=64, verifier_layers=6, sa_cfg=SA_CFG, chunk_frags=32):
         if not torch.cuda.is_available():
@@ -57,6 +60,7 @@ class Engine:
         self.ver = VerifierWeights(ckpt["verifier"], self.device, verifier_layers) if "verifier" in ckpt else None
         self.C = self.den.C
         self.tc_attention = True  # tcgen05 global attention in bf16 mode (segments <= 512 tokens)
+        self.fused_sa = True     # fused gather + 3-layer MLP + max tcgen05 kernel in bf16 mode
         self._ws = {}
 
     # ------------------------------------------------------------------ helpers
@@ -121,9 +125,22 @@ class Engine:
                      ns, gidx.data_ptr())
                 rows = K * S * ns
                 ld = kin[li]
+                l0, l1, l2 = self.enc.sa[li]
+                if self.bf16 and self.fused_sa and (ns, src_d, l0.n, l1.n, l2.n) in self._FUSED_LEVELS:
+                    call("pfpp_sa_fused", self._FUSED_LEVELS[(ns, src_d, l0.n, l1.n, l2.n)], src_xyz.data_ptr(),
+                         cx.data_ptr(), _lib.ptr(src_feat), gidx.data_ptr(), K, src_n, S, l0.w16_fused.data_ptr(),
+                         l0.k0_fused, l0.b.data_ptr(), l1.w16.data_ptr(), l1.b.data_ptr(), l2.w16.data_ptr(),
+                         l2.b.data_ptr(), feats[li].data_ptr())
+                    if trace is not None:
+                        trace.setdefault(f"sa{li + 1}.fps_idx", []).append(idx[li][:K].clone())
+                        trace.setdefault(f"sa{li + 1}.group_idx", []).append(gidx[:rows].view(K, S, ns).clone())
+                        trace.setdefault(f"sa{li + 1}.feats", []).append(feats[li][:K].float().clone())
+                        if li == 0:
+                            trace.setdefault("rotated", []).append(rot[:K].clone())
+                    src_xyz, src_n, src_feat, src_d = cx, S, feats[li], l2.n
+                    continue
                 call("pfpp_group_gather", src_xyz.data_ptr(), cx.data_ptr(), _lib.ptr(src_feat), gidx.data_ptr(), K,
                      src_n, S, ns, src_d, ld, bf, X.data_ptr())
-                l0, l1, l2 = self.enc.sa[li]
                 self.gemm(X, ld, l0, B1, l0.n, rows, EPI_RELU)
                 self.gemm(B1, l0.n, l1, B2, l1.n, rows, EPI_RELU)
                 self.gemm(B2, l1.n, l2, B3, l2.n, rows, EPI_RELU)

@@ -62,6 +62,17 @@ class EncoderWeights:
                 w, b = fold_bn(sd, f"pn2.sa{li + 1}", i)
                 layers.append(Linear(w, b, device, bf16))
             self.sa.append(layers)
+            if bf16:
+                # layer-0 weight for the fused kernel: columns [feats(D) | dx dy dz | 0-pad to 16]
+                w0 = layers[0]
+                d = w0.k - 3
+                k0 = (w0.k + 15) // 16 * 16
+                wf = torch.zeros(w0.n, k0)
+                w = fold_bn(sd, f"pn2.sa{li + 1}", 0)[0]
+                wf[:, :d] = w[:, 3:]
+                wf[:, d:d + 3] = w[:, :3]
+                w0.w16_fused = wf.to(device).to(torch.bfloat16).contiguous()
+                w0.k0_fused = k0
         self.conv6 = Linear(sd["pn2.conv6.weight"].flatten(1), sd["pn2.conv6.bias"], device, bf16)
         self.codebook = sd["vector_quantization.embedding.weight"].detach().float().contiguous().to(device)
 

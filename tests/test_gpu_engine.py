@@ -199,3 +199,20 @@ def test_metrics_block_vs_reference_golden():
         ref = torch.stack([g["acc"][0], g["rmse_r"][0], g["rmse_t"][0], g["cd"][0]])
         assert m[0] == ref[0]
         assert torch.allclose(m[1:], ref[1:], rtol=1e-4), (m, ref)
+
+
+def test_fused_sa_matches_unfused(engines, ckpt):
+    """fused tcgen05 set-abstraction kernel vs the unfused (gather, 3 GEMMs, max) bf16 path: same bf16
+    rounding points, so features agree to bf16 resolution (1e-2 of the feature scale) at every level."""
+    e = engines("bf16", 20)
+    outs = {}
+    for fused in (True, False):
+        e.fused_sa = fused
+        _, latent, xyz, tr = _encode_golden(e)
+        outs[fused] = tr
+    e.fused_sa = True
+    for lvl in ("sa1", "sa2", "sa3"):
+        a, b = outs[True][f"{lvl}.feats"][0].cpu(), outs[False][f"{lvl}.feats"][0].cpu()
+        assert torch.equal(outs[True][f"{lvl}.group_idx"][0].cpu(), outs[False][f"{lvl}.group_idx"][0].cpu())
+        rel = (a - b).abs().max() / b.abs().max()
+        assert rel <= 1e-2, (lvl, rel)
