@@ -89,12 +89,12 @@ int pfpp_vq(const void* z, int z_is_bf16, long long n_chunks, const float* codeb
 /* sample_and_group's gather + PointNetSetAbstraction's 3 x relu(bn(conv1x1)) + max over nsample
  * (utils/pn2_utils.py:139-148,209-214) fused in one tcgen05 kernel; activations stay in shared
  * memory / TMEM.  level in {1,2,3} selects (nsample, D, C1, C2, C3) = (32,0,64,64,128),
- * (64,128,128,128,256), (64,256,256,256,512).  feats [K,N,D] bf16; w0 [C1, ldw0] bf16 with columns
- * ordered [feats(D) | dx dy dz | 0-pad to a multiple of 16]; w1 [C2,C1], w2 [C3,C2] bf16 (BN folded);
- * out [K*S, C3] bf16. */
+ * (64,128,128,128,256), (64,256,256,256,512).  feats [K,N,D] bf16.  Layer 0 is split: w0_feat [C1, D]
+ * bf16 (feature columns, tensor cores; NULL for level 1) and w0_xyz [C1, 4] fp32 (dx,dy,dz columns, applied
+ * as fp32 FMAs in the epilogue); w1 [C2,C1], w2 [C3,C2] bf16; all with BatchNorm folded; out [K*S, C3] bf16. */
 int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K, int N,
-                  int S, const void* w0, int ldw0, const float* b0, const void* w1, const float* b1, const void* w2,
-                  const float* b2, void* out, cudaStream_t stream);
+                  int S, const void* w0_feat, const float* w0_xyz, const float* b0, const void* w1, const float* b1,
+                  const void* w2, const float* b2, void* out, cudaStream_t stream);
 
 /* ---- contractions ---------------------------------------------------------------------- */
 
@@ -143,9 +143,11 @@ int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_off, int v_o
 /* The denoiser's global attention (attention.py:84: diffusers Attention with the key mask) on the
  * tensor cores: bf16 qkv [M, 3C] (q | k | v, head h at columns h*64), segments of <= 512 tokens,
  * head_dim 64; S = QK^T and O = PV run as tcgen05.mma with fp32 accumulators in TMEM, operands by TMA.
- * out is bf16 [M, C]. */
+ * block > 0 additionally restricts attention to aligned blocks of `block` tokens inside a segment:
+ * the block-diagonal local attention (attention.py:79 with self_mask, denoiser_transformer.py:158-166),
+ * run on segments of 5 fragments (125 tokens).  out is bf16 [M, C]. */
 int pfpp_attention_tc(const void* qkv, long long M, int ld, int C, const int* seg_start, const int* seg_len,
-                      int n_segments, int max_len, int heads, void* out, int ldo, cudaStream_t stream);
+                      int n_segments, int max_len, int heads, int block, void* out, int ldo, cudaStream_t stream);
 
 /* mean over L (denoiser_transformer.py:141-142). */
 int pfpp_mean_pool(const float* h, int F, int L, int C, int out_bf16, void* out, cudaStream_t stream);

@@ -29,7 +29,7 @@ SIGNATURES = {
     "pfpp_ball_query": [_P, _P, _I, _I, _I, _F, _I, _P, _P],
     "pfpp_group_gather": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "pfpp_group_max": [_P, _L, _I, _I, _I, _I, _P, _I, _P],
-    "pfpp_sa_fused": [_I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "pfpp_sa_fused": [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pfpp_vq": [_P, _I, _L, _P, _I, _P, _P, _P],
     "pfpp_gemm_f32": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "pfpp_gemm_bf16": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
@@ -37,7 +37,7 @@ SIGNATURES = {
     "pfpp_combine_embed": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "pfpp_layernorm": [_P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _P, _P, _P],
     "pfpp_attention_varlen": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
-    "pfpp_attention_tc": [_P, _L, _I, _I, _P, _P, _I, _I, _I, _P, _I, _P],
+    "pfpp_attention_tc": [_P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P],
     "pfpp_mean_pool": [_P, _I, _I, _I, _I, _P, _P],
     "pfpp_ddpm_step": [_P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P],
     "pfpp_pose_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P],

@@ -111,8 +111,8 @@ constexpr uint32_t AT_IDESC_O =
 
 __global__ void __launch_bounds__(128)
     attention_tc_kernel(const __grid_constant__ CUtensorMap map, const int* __restrict__ seg_start,
-                        const int* __restrict__ seg_len, int C, float scale_log2e, __nv_bfloat16* __restrict__ out,
-                        int ldo) {
+                        const int* __restrict__ seg_len, int C, float scale_log2e, int block,
+                        __nv_bfloat16* __restrict__ out, int ldo) {
   const int seg = blockIdx.z, h = blockIdx.y;
   const int len = seg_len[seg], st = seg_start[seg];
   const int q0 = blockIdx.x * AT_BQ;
@@ -168,16 +168,25 @@ __global__ void __launch_bounds__(128)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
   const int row = warp * 32 + lane;
+  // key k is visible to query q iff k < len and (no block structure or same block): block > 0 gives the
+  // block-diagonal local attention (one 25-token block per fragment, denoiser_transformer.py:158-166)
+  int klo = 0, khi = len;
+  if (block > 0) {
+    klo = ((q0 + row) / block) * block;
+    khi = min(len, klo + block);
+  }
   float mx = -INFINITY;
   for (int c = 0; c < nkb * (AT_BK / 32); ++c) {
     uint32_t v[32];
     tmem_ld32(lane_addr + c * 32, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(v[j]));
+    for (int j = 0; j < 32; ++j) {
+      const int key = c * 32 + j;
+      if (key >= klo && key < khi) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
   }
-  const float mxs = mx * scale_log2e;
+  const float mxs = (mx == -INFINITY) ? 0.f : mx * scale_log2e;
   float sum = 0.f;
   for (int kb = 0; kb < nkb; ++kb) {
     const int pb = kb & 1;
@@ -192,8 +201,8 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
         int key = kb * AT_BK + c * 32 + j;
-        float p0 = key < len ? exp2f(__uint_as_float(v[j]) * scale_log2e - mxs) : 0.f;
-        float p1 = key + 1 < len ? exp2f(__uint_as_float(v[j + 1]) * scale_log2e - mxs) : 0.f;
+        float p0 = (key >= klo && key < khi) ? exp2f(__uint_as_float(v[j]) * scale_log2e - mxs) : 0.f;
+        float p1 = (key + 1 >= klo && key + 1 < khi) ? exp2f(__uint_as_float(v[j + 1]) * scale_log2e - mxs) : 0.f;
         __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
         // the row sum uses the bf16-rounded probabilities that the PV product actually sees
         sum += __low2float(b2) + __high2float(b2);
@@ -276,7 +285,8 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }  // namespace
 
 extern "C" int pfpp_attention_tc(const void* qkv, long long M, int ld, int C, const int* seg_start, const int* seg_len,
-                                 int n_segments, int max_len, int heads, void* out, int ldo, cudaStream_t stream) {
+                                 int n_segments, int max_len, int heads, int block, void* out, int ldo,
+                                 cudaStream_t stream) {
   PFPP_CHECK_ARG(qkv && seg_start && seg_len && out && heads > 0 && C == heads * AT_D);
   PFPP_CHECK_ARG(max_len <= AT_MAXKB * AT_BK && (ld % 8) == 0 && (ldo % 8) == 0 && ((uintptr_t)qkv & 15) == 0 &&
                  ((uintptr_t)out & 15) == 0);
@@ -295,7 +305,7 @@ extern "C" int pfpp_attention_tc(const void* qkv, long long M, int ld, int C, co
   cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
   dim3 grid(pfpp_cdiv(max_len, AT_BQ), heads, n_segments);
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)AT_D);
-  attention_tc_kernel<<<grid, 128, AT_SMEM_BYTES, stream>>>(map, seg_start, seg_len, C, scale_log2e,
+  attention_tc_kernel<<<grid, 128, AT_SMEM_BYTES, stream>>>(map, seg_start, seg_len, C, scale_log2e, block,
                                                            (__nv_bfloat16*)out, ldo);
   PFPP_RETURN_LAST();
 }

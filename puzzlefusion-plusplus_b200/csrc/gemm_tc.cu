@@ -190,17 +190,33 @@ __global__ void __launch_bounds__(128)
     const int nb = n0 + c * 32;
     if (row < M && nb < N) {
       if (EPI == PFPP_EPI_GEGLU) {
-        // interleaved (value, gate) column pairs -> 16 outputs at columns nb/2 ..
+        // interleaved (value, gate) column pairs -> 16 outputs at columns nb/2 .. nb/2+15
+        float o[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          int n = nb + j;
-          if (n + 1 < N) {
-            float val = __uint_as_float(v[j]) + (bias ? bias[n] : 0.f);
-            float gate = __uint_as_float(v[j + 1]) + (bias ? bias[n + 1] : 0.f);
-            float o = val * gelu_erf(gate);
-            size_t off = (size_t)row * ldc + (n >> 1);
-            if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(Cout)[off] = __float2bfloat16_rn(o);
-            else reinterpret_cast<float*>(Cout)[off] = o;
+          const int n = nb + j;
+          float val = __uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f);
+          float gate = __uint_as_float(v[j + 1]) + ((bias && n + 1 < N) ? bias[n + 1] : 0.f);
+          o[j >> 1] = val * gelu_erf(gate);
+        }
+        const size_t off = (size_t)row * ldc + (nb >> 1);
+        if (nb + 32 <= N && OUT_BF16 && (ldc % 8) == 0) {
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + off;
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            uint4 pk;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(cp + j) = pk;
+          }
+        } else {
+          for (int j = 0; j < 16; ++j) {
+            if (nb + 2 * j + 1 < N) {
+              if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(Cout)[off + j] = __float2bfloat16_rn(o[j]);
+              else reinterpret_cast<float*>(Cout)[off + j] = o[j];
+            }
           }
         }
       } else {
@@ -212,9 +228,18 @@ __global__ void __launch_bounds__(128)
           o[j] = tc_act<EPI>(t);
         }
         if (residual) {
+          const float* rp = residual + (size_t)row * ldr + nb;
+          if (nb + 32 <= N && (ldr % 4) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < N) o[j] += residual[(size_t)row * ldr + nb + j];
+            for (int j = 0; j < 32; j += 4) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+              o[j] += r4.x, o[j + 1] += r4.y, o[j + 2] += r4.z, o[j + 3] += r4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < N) o[j] += rp[j];
+          }
         }
         if (OUT_BF16) {
           __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * ldc + nb;

@@ -15,8 +15,9 @@
 // layer boundaries; X tiles are written by the CTA's own threads (generic proxy) and published to the
 // tensor core with fence.proxy.async.
 //
-// Column order of layer 0 is [feats(D) | dx dy dz | 0-pad] (the host permutes W0 accordingly) so that
-// feature rows are gathered with aligned 16-byte loads/stores.
+// Layer 0 is split: the D feature columns go through the tensor cores (aligned 16-byte gathers), the three
+// centroid-offset columns (dx,dy,dz) are added in the epilogue as fp32 FMAs by the thread that owns the row
+// -- exact fp32 geometry terms, no padded K panel, and the first level (D = 0) needs no layer-0 MMA at all.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -101,6 +102,7 @@ struct SaParams {
   const float* new_xyz;    // [K, S, 3] centroids
   const __nv_bfloat16* feats;  // [K, N, D] previous level features (nullptr when D == 0)
   const int* gidx;         // [K, S, NS]
+  const float* wxyz;       // [C1, 4] fp32: layer-0 weights of the (dx,dy,dz) columns, applied in the epilogue
   const float* b0;
   const float* b1;
   const float* b2;
@@ -111,17 +113,19 @@ struct SaParams {
 
 template <int NS, int D, int C1, int C2, int C3, int STAGES>
 struct SaCfg {
-  static constexpr int K0 = ((D + 3 + 15) / 16) * 16;       // layer-0 K, multiple of UMMA_K
-  static constexpr int P0 = (K0 + 63) / 64;                 // panels of X0
+  static constexpr int K0 = D;                              // layer-0 tensor-core K (feature columns only)
+  static constexpr int P0 = D / 64;                         // panels of X0 (0 for the first level)
   static constexpr int P1 = (C1 + 63) / 64, P2 = (C2 + 63) / 64;
   static constexpr int NB1 = (C1 + 127) / 128, NB2 = (C2 + 127) / 128, MB3 = C3 / 128;
-  static constexpr int XA_PANELS = (P0 > P2 ? P0 : P2);     // X0 and X2 share a buffer
-  static constexpr uint32_t OFF_XA = 0;
-  static constexpr uint32_t OFF_XB = XA_PANELS * SF_TILE;   // X1
-  static constexpr uint32_t OFF_W = OFF_XB + P1 * SF_TILE;
+  static constexpr int X_PANELS = (P0 > P1 ? (P0 > P2 ? P0 : P2) : (P1 > P2 ? P1 : P2));
+  static constexpr uint32_t OFF_X = 0;                      // X0 -> X1 -> X2 in place
+  static constexpr uint32_t OFF_W = X_PANELS * SF_TILE;
   static constexpr uint32_t OFF_BAR = OFF_W + STAGES * SF_TILE;
-  static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;
-  static constexpr int TMEM_COLS = (C3 > 256 || C1 > 256 || C2 > 256) ? 512 : ((C3 > 128 || C1 > 128 || C2 > 128) ? 256 : 128);
+  static constexpr uint32_t OFF_ROWS = OFF_BAR + 128;        // [128] int64 gather offsets
+  static constexpr uint32_t OFF_CONST = OFF_ROWS + 1024;     // wxyz [C1][4] | b0 [C1] | b1 [C2] | b2 [C3]  (fp32)
+  static constexpr uint32_t CONST_BYTES = (C1 * 5 + C2 + C3) * 4;
+  static constexpr uint32_t SMEM = OFF_CONST + CONST_BYTES + 1024 /*align slack*/;
+  static constexpr int TMEM_COLS = (C1 > 128 || C2 > 128) ? 256 : 128;
   static constexpr int G = 128 / NS;                        // groups per CTA
 };
 
@@ -170,8 +174,9 @@ __global__ void __launch_bounds__(160)
       tma_load_2d(base + Cfg::OFF_W + s * SF_TILE, m, bar_full + 8 * s, kcol, row);
       ++it;
     };
-    for (int nb = 0; nb < Cfg::NB1; ++nb)
-      for (int kp = 0; kp < Cfg::P0; ++kp) push(&map_w0, kp * 64, nb * 128);
+    if (D > 0)
+      for (int nb = 0; nb < Cfg::NB1; ++nb)
+        for (int kp = 0; kp < Cfg::P0; ++kp) push(&map_w0, kp * 64, nb * 128);
     for (int nb = 0; nb < Cfg::NB2; ++nb)
       for (int kp = 0; kp < Cfg::P1; ++kp) push(&map_w1, kp * 64, nb * 128);
     for (int mb = 0; mb < Cfg::MB3; ++mb)
@@ -179,31 +184,57 @@ __global__ void __launch_bounds__(160)
     return;  // the ring drains on its own; shared memory stays live until the compute warps exit
   }
 
-  // ---------------- gather: X0[row] = [feats[idx] | xyz[idx]-centroid | 0] (bf16, swizzled) ----------
+  float d3[3] = {0.f, 0.f, 0.f};  // this thread's row: xyz[idx] - centroid (fp32, used by the layer-0 epilogue)
+  // ---------------- gather: X0[row] = feats[idx] (bf16, swizzled) ----------
+  // phase 1: thread = row -> neighbour index, xyz offset columns; phase 2: all 128 threads stream the
+  // feature rows as 16-byte chunks (consecutive threads = consecutive chunks of a row), 8 loads in flight.
   {
-    uint8_t* xa = bp + Cfg::OFF_XA;
-    // zero the tail panel columns that the MMA will read beyond D+3 (K0 is a multiple of 16)
-    for (int r = warp; r < 128; r += 4) {
+    uint8_t* xa = bp + Cfg::OFF_X;
+    long long* src_row = reinterpret_cast<long long*>(bp + Cfg::OFF_ROWS);  // [128] element offsets, -1 = padding
+    (void)xa;
+    {
+      const int r = threadIdx.x;
       const long long g = g0 + r / NS;
       const bool valid = g < p.groups;
-      int idx = 0;
-      long long k = 0;
+      long long off = -1;
       if (valid) {
-        idx = p.gidx[g * NS + (r % NS)];
-        k = g / p.S;
+        const int idx = p.gidx[g * NS + (r % NS)];
+        const long long k = g / p.S;
+        off = k * p.N + idx;
+        const float* px = p.xyz + off * 3;
+        const float* pc = p.new_xyz + g * 3;
+        d3[0] = fsub(px[0], pc[0]), d3[1] = fsub(px[1], pc[1]), d3[2] = fsub(px[2], pc[2]);
       }
-      if (D > 0) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.feats + ((size_t)k * p.N + idx) * D);
-        for (int c8 = lane; c8 < D / 8; c8 += 32) {
-          uint4 v = valid ? src[c8] : make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(xa + xoff(r, c8 * 8)) = v;
+      src_row[r] = off;
+    }
+    {  // per-channel constants -> shared memory (broadcast LDS in the epilogues instead of dependent LDGs)
+      float* cst = reinterpret_cast<float*>(bp + Cfg::OFF_CONST);
+      for (int i = threadIdx.x; i < C1 * 4; i += 128) cst[i] = p.wxyz[i];
+      for (int i = threadIdx.x; i < C1; i += 128) cst[C1 * 4 + i] = p.b0[i];
+      for (int i = threadIdx.x; i < C2; i += 128) cst[C1 * 5 + i] = p.b1[i];
+      for (int i = threadIdx.x; i < C3; i += 128) cst[C1 * 5 + C2 + i] = p.b2[i];
+    }
+    if (D > 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      constexpr int CPR = D / 8;                 // 16-byte chunks per row
+      constexpr int TOTAL = 128 * CPR;
+      constexpr int UNR = 8;
+      static_assert(TOTAL % (128 * UNR) == 0, "gather unroll");
+      for (int i0 = threadIdx.x; i0 < TOTAL; i0 += 128 * UNR) {
+        uint4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int ch = i0 + u * 128;
+          const int r = ch / CPR, c8 = ch % CPR;
+          const long long off = src_row[r];
+          v[u] = off >= 0 ? reinterpret_cast<const uint4*>(p.feats + off * D)[c8] : make_uint4(0, 0, 0, 0);
         }
-      }
-      // tail: columns D .. K0-1 (xyz offsets then zeros); K0 - D <= 16
-      if (lane < Cfg::K0 - D) {
-        float v = 0.f;
-        if (valid && lane < 3) v = fsub(p.xyz[((size_t)k * p.N + idx) * 3 + lane], p.new_xyz[g * 3 + lane]);
-        *reinterpret_cast<__nv_bfloat16*>(xa + xoff(r, D + lane)) = __float2bfloat16_rn(v);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int ch = i0 + u * 128;
+          const int r = ch / CPR, c8 = ch % CPR;
+          *reinterpret_cast<uint4*>(xa + xoff(r, c8 * 8)) = v[u];
+        }
       }
     }
   }
@@ -217,14 +248,15 @@ __global__ void __launch_bounds__(160)
   // ---------------- layers 0 and 1: rows on M ----------------
 #pragma unroll
   for (int layer = 0; layer < 2; ++layer) {
-    const int KSTEPS = layer == 0 ? Cfg::K0 / 16 : C1 / 16;
     const int PANELS = layer == 0 ? Cfg::P0 : Cfg::P1;
     const int NB = layer == 0 ? Cfg::NB1 : Cfg::NB2;
     const int COUT = layer == 0 ? C1 : C2;
-    const uint32_t xin = base + (layer == 0 ? Cfg::OFF_XA : Cfg::OFF_XB);
-    uint8_t* xout = bp + (layer == 0 ? Cfg::OFF_XB : Cfg::OFF_XA);
-    const float* bias = layer == 0 ? p.b0 : p.b1;
-    if (threadIdx.x == 32) {
+    const uint32_t xin = base + Cfg::OFF_X;
+    uint8_t* xout = bp + Cfg::OFF_X;
+    const float* cst = reinterpret_cast<const float*>(bp + Cfg::OFF_CONST);
+    const float* bias = cst + (layer == 0 ? C1 * 4 : C1 * 5);
+    const bool has_mma = !(layer == 0 && D == 0);
+    if (has_mma && threadIdx.x == 32) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int nb = 0; nb < NB; ++nb) {
         for (int kp = 0; kp < PANELS; ++kp) {
@@ -232,7 +264,7 @@ __global__ void __launch_bounds__(160)
           mbar_wait(bar_full + 8 * s, (w_it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = desc_kmajor(xin + kp * SF_TILE), db = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE);
-          const int ks = min(4, KSTEPS - kp * 4);
+          const int ks = 4;
           for (int k = 0; k < ks; ++k) umma_bf16(tmem + nb * 128, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
           umma_commit(bar_empty + 8 * s);
           ++w_it;
@@ -241,17 +273,31 @@ __global__ void __launch_bounds__(160)
       umma_commit(bar_acc);
     }
     __syncwarp();
-    mbar_wait(bar_acc, acc_phase);
-    acc_phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // epilogue: thread = row; bias + ReLU -> bf16 -> next operand tile
+    if (has_mma) {
+      mbar_wait(bar_acc, acc_phase);
+      acc_phase ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // epilogue: thread = row; (+ xyz terms) + bias + ReLU -> bf16 -> next operand tile
     const int row = warp * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c = 0; c < COUT / 32; ++c) {
       uint32_t v[32];
-      tmem_ld32(lane_addr + c * 32, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (has_mma) {
+        tmem_ld32(lane_addr + c * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (layer == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(cst + (c * 32 + j) * 4);
+          v[j] = __float_as_uint(fmaf(w.z, d3[2], fmaf(w.y, d3[1], fmaf(w.x, d3[0], __uint_as_float(v[j])))));
+        }
+      }
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
@@ -269,40 +315,39 @@ __global__ void __launch_bounds__(160)
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
 
-  // ---------------- layer 2: channels on M, rows on N; max over each group's columns ----------------
-  if (threadIdx.x == 32) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t xin = base + Cfg::OFF_XA;
-    for (int mb = 0; mb < Cfg::MB3; ++mb) {
-      for (int kp = 0; kp < Cfg::P2; ++kp) {
-        const int s = w_it % STAGES;
-        mbar_wait(bar_full + 8 * s, (w_it / STAGES) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE), db = desc_kmajor(xin + kp * SF_TILE);
-        const int ks = min(4, C2 / 16 - kp * 4);
-        for (int k = 0; k < ks; ++k) umma_bf16(tmem + mb * 128, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
-        umma_commit(bar_empty + 8 * s);
-        ++w_it;
-      }
-    }
-    umma_commit(bar_acc);
-  }
-  __syncwarp();
-  mbar_wait(bar_acc, acc_phase);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // ---------------- layer 2: channels on M (one 128-channel block at a time), rows on N ----------------
   {
+    const uint32_t xin = base + Cfg::OFF_X;
+    const float* b2s = reinterpret_cast<const float*>(bp + Cfg::OFF_CONST) + C1 * 5 + C2;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int mb = 0; mb < Cfg::MB3; ++mb) {
+      if (threadIdx.x == 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kp = 0; kp < Cfg::P2; ++kp) {
+          const int s = w_it % STAGES;
+          mbar_wait(bar_full + 8 * s, (w_it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE), db = desc_kmajor(xin + kp * SF_TILE);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
+          umma_commit(bar_empty + 8 * s);
+          ++w_it;
+        }
+        umma_commit(bar_acc);
+      }
+      __syncwarp();
+      mbar_wait(bar_acc, acc_phase);
+      acc_phase ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int ch = mb * 128 + warp * 32 + lane;
-      const float bias = p.b2[ch];
+      const float bias = b2s[ch];
 #pragma unroll 1
       for (int g = 0; g < Cfg::G; ++g) {
         float m = -INFINITY;
 #pragma unroll
         for (int c = 0; c < NS / 32; ++c) {
           uint32_t v[32];
-          tmem_ld32(lane_addr + mb * 128 + g * NS + c * 32, v);
+          tmem_ld32(lane_addr + g * NS + c * 32, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
@@ -310,6 +355,9 @@ __global__ void __launch_bounds__(160)
         const long long grp = g0 + g;
         if (grp < p.groups) p.out[grp * C3 + ch] = __float2bfloat16_rn(fmaxf(m + bias, 0.f));
       }
+      // the next channel block reuses the same TMEM columns: all four warps must have drained them
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -343,10 +391,11 @@ int weight_map(CUtensorMap* map, const void* w, int rows, int cols, int ld) {
 }
 
 template <int NS, int D, int C1, int C2, int C3, int STAGES>
-int launch_sa(const SaParams& p, const void* w0, int ldw0, const void* w1, const void* w2, cudaStream_t stream) {
+int launch_sa(const SaParams& p, const void* w0, const void* w1, const void* w2, cudaStream_t stream) {
   using Cfg = SaCfg<NS, D, C1, C2, C3, STAGES>;
+  static_assert(D % 64 == 0 && C1 % 64 == 0 && C2 % 64 == 0 && C3 % 128 == 0, "panel-aligned channel counts");
   CUtensorMap m0, m1, m2;
-  int rc = weight_map(&m0, w0, C1, Cfg::K0, ldw0);
+  int rc = D > 0 ? weight_map(&m0, w0, C1, D, D) : weight_map(&m0, w1, C2, C1, C1);  // m0 unused when D == 0
   if (rc) return rc;
   rc = weight_map(&m1, w1, C2, C1, C1);
   if (rc) return rc;
@@ -362,20 +411,21 @@ int launch_sa(const SaParams& p, const void* w0, int ldw0, const void* w1, const
 }  // namespace
 
 extern "C" int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K,
-                             int N, int S, const void* w0, int ldw0, const float* b0, const void* w1, const float* b1,
-                             const void* w2, const float* b2, void* out, cudaStream_t stream) {
-  PFPP_CHECK_ARG(xyz && new_xyz && gidx && w0 && w1 && w2 && b0 && b1 && b2 && out && K >= 0 && (ldw0 % 8) == 0);
+                             int N, int S, const void* w0_feat, const float* w0_xyz, const float* b0, const void* w1,
+                             const float* b1, const void* w2, const float* b2, void* out, cudaStream_t stream) {
+  PFPP_CHECK_ARG(xyz && new_xyz && gidx && w0_xyz && w1 && w2 && b0 && b1 && b2 && out && K >= 0);
   if (K == 0) return PFPP_OK;
-  SaParams p{xyz, new_xyz, (const __nv_bfloat16*)feats, gidx, b0, b1, b2, (__nv_bfloat16*)out, N, S, (long long)K * S};
+  SaParams p{xyz, new_xyz, (const __nv_bfloat16*)feats, gidx, w0_xyz, b0, b1, b2, (__nv_bfloat16*)out, N, S,
+             (long long)K * S};
   switch (level) {
     case 1:
-      return launch_sa<32, 0, 64, 64, 128, 2>(p, w0, ldw0, w1, w2, stream);
+      return launch_sa<32, 0, 64, 64, 128, 2>(p, w0_feat, w1, w2, stream);
     case 2:
-      PFPP_CHECK_ARG(feats);
-      return launch_sa<64, 128, 128, 128, 256, 4>(p, w0, ldw0, w1, w2, stream);
+      PFPP_CHECK_ARG(feats && w0_feat);
+      return launch_sa<64, 128, 128, 128, 256, 2>(p, w0_feat, w1, w2, stream);
     case 3:
-      PFPP_CHECK_ARG(feats);
-      return launch_sa<64, 256, 256, 256, 512, 4>(p, w0, ldw0, w1, w2, stream);
+      PFPP_CHECK_ARG(feats && w0_feat);
+      return launch_sa<64, 256, 256, 256, 512, 2>(p, w0_feat, w1, w2, stream);
     default:
       return PFPP_EINVAL;
   }

@@ -85,6 +85,17 @@ class Engine:
             call("pfpp_gemm_f32", a.data_ptr(), lda, lin.w32.data_ptr(), lin.k32, bias, res, ldr, out.data_ptr(), ldc,
                  M, lin.n, lin.k32, epi)
 
+    def _local_tc_segments(self, F):
+        """segments of 5 fragments for the block-diagonal tensor-core attention (cached per F)."""
+        key = ("loc_tc", F)
+        if key not in self._ws:
+            L = self.L
+            n = (F + 4) // 5
+            start = torch.arange(n, dtype=torch.int32, device=self.device) * (5 * L)
+            length = torch.clamp(F * L - start, max=5 * L).to(torch.int32)
+            self._ws[key] = (start, length)
+        return self._ws[key]
+
     def _pad(self, k):
         return (k + self.kmult - 1) // self.kmult * self.kmult
 
@@ -96,7 +107,9 @@ class Engine:
         z_e = self.buf("z_e", (F * L, self.latent_dim), torch.float32)
         xyz_out = self.buf("xyz3", (F, L, 3), torch.float32)
         latent = self.buf("latent", (F * L, self.latent_dim), torch.float32)
-        Fc = min(self.chunk, F)
+        # the fused path keeps activations on chip, so nothing needs chunking; the unfused path bounds its
+        # [rows, C] intermediates by processing `chunk` fragments at a time
+        Fc = F if (self.bf16 and self.fused_sa) else min(self.chunk, F)
         rot = self.buf("rot", (Fc, N, 3), torch.float32)
         max_rows = Fc * max(s * ns for s, _, ns in self.sa_cfg)
         gidx = self.buf("gidx", (max_rows,), torch.int32)
@@ -128,8 +141,8 @@ class Engine:
                 l0, l1, l2 = self.enc.sa[li]
                 if self.bf16 and self.fused_sa and (ns, src_d, l0.n, l1.n, l2.n) in self._FUSED_LEVELS:
                     call("pfpp_sa_fused", self._FUSED_LEVELS[(ns, src_d, l0.n, l1.n, l2.n)], src_xyz.data_ptr(),
-                         cx.data_ptr(), _lib.ptr(src_feat), gidx.data_ptr(), K, src_n, S, l0.w16_fused.data_ptr(),
-                         l0.k0_fused, l0.b.data_ptr(), l1.w16.data_ptr(), l1.b.data_ptr(), l2.w16.data_ptr(),
+                         cx.data_ptr(), _lib.ptr(src_feat), gidx.data_ptr(), K, src_n, S, _lib.ptr(l0.w16_feat),
+                         l0.wxyz.data_ptr(), l0.b.data_ptr(), l1.w16.data_ptr(), l1.b.data_ptr(), l2.w16.data_ptr(),
                          l2.b.data_ptr(), feats[li].data_ptr())
                     if trace is not None:
                         trace.setdefault(f"sa{li + 1}.fps_idx", []).append(idx[li][:K].clone())
@@ -204,7 +217,12 @@ class Engine:
                 self.gemm(ln, C, lw[name + ".qkv"], qkv, 3 * C, M)
                 if self.bf16 and which == 1 and mlen <= 512 and D == 64 and self.tc_attention:
                     call("pfpp_attention_tc", qkv.data_ptr(), M, 3 * C, C, segs[0].data_ptr(), segs[1].data_ptr(), nseg,
-                         mlen, H, ao.data_ptr(), C)
+                         mlen, H, 0, ao.data_ptr(), C)
+                elif self.bf16 and which == 0 and D == 64 and self.tc_attention and 5 * L <= 128:
+                    # block-diagonal local attention: 5 fragments (125 tokens) per 128-row tensor-core tile
+                    ts, tl = self._local_tc_segments(F)
+                    call("pfpp_attention_tc", qkv.data_ptr(), M, 3 * C, C, ts.data_ptr(), tl.data_ptr(), ts.numel(),
+                         5 * L, H, L, ao.data_ptr(), C)
                 else:
                     call("pfpp_attention_varlen", qkv.data_ptr(), 3 * C, 0, C, 2 * C, segs[0].data_ptr(),
                          segs[1].data_ptr(), nseg, mlen, H, D, bf, ao.data_ptr(), C)

@@ -63,16 +63,14 @@ class EncoderWeights:
                 layers.append(Linear(w, b, device, bf16))
             self.sa.append(layers)
             if bf16:
-                # layer-0 weight for the fused kernel: columns [feats(D) | dx dy dz | 0-pad to 16]
+                # layer 0 of the fused kernel: feature columns on the tensor cores (bf16), the three
+                # centroid-offset columns as fp32 epilogue FMAs
                 w0 = layers[0]
-                d = w0.k - 3
-                k0 = (w0.k + 15) // 16 * 16
-                wf = torch.zeros(w0.n, k0)
                 w = fold_bn(sd, f"pn2.sa{li + 1}", 0)[0]
-                wf[:, :d] = w[:, 3:]
-                wf[:, d:d + 3] = w[:, :3]
-                w0.w16_fused = wf.to(device).to(torch.bfloat16).contiguous()
-                w0.k0_fused = k0
+                w0.w16_feat = w[:, 3:].contiguous().to(device).to(torch.bfloat16) if w.shape[1] > 3 else None
+                wx = torch.zeros(w0.n, 4)
+                wx[:, :3] = w[:, :3]
+                w0.wxyz = wx.contiguous().to(device)
         self.conv6 = Linear(sd["pn2.conv6.weight"].flatten(1), sd["pn2.conv6.bias"], device, bf16)
         self.codebook = sd["vector_quantization.embedding.weight"].detach().float().contiguous().to(device)
 

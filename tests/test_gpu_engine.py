@@ -202,17 +202,23 @@ def test_metrics_block_vs_reference_golden():
 
 
 def test_fused_sa_matches_unfused(engines, ckpt):
-    """fused tcgen05 set-abstraction kernel vs the unfused (gather, 3 GEMMs, max) bf16 path: same bf16
-    rounding points, so features agree to bf16 resolution (1e-2 of the feature scale) at every level."""
+    """fused tcgen05 set-abstraction kernel vs the unfused (gather, 3 GEMMs, max) bf16 path and the fp32
+    oracle: identical grouping indices; features within 3e-2 of the feature scale of the oracle at every
+    level (bf16 operands), and no worse than the unfused bf16 path (the fused kernel keeps the centroid
+    offsets in fp32)."""
     e = engines("bf16", 20)
     outs = {}
     for fused in (True, False):
         e.fused_sa = fused
-        _, latent, xyz, tr = _encode_golden(e)
+        g, latent, xyz, tr = _encode_golden(e)
         outs[fused] = tr
     e.fused_sa = True
+    otr = {}
+    oe.vqvae_encode(ckpt["encoder"], g["rotated"], trace=otr)
     for lvl in ("sa1", "sa2", "sa3"):
-        a, b = outs[True][f"{lvl}.feats"][0].cpu(), outs[False][f"{lvl}.feats"][0].cpu()
+        a, b, o = outs[True][f"{lvl}.feats"][0].cpu(), outs[False][f"{lvl}.feats"][0].cpu(), otr[f"{lvl}.feats"]
         assert torch.equal(outs[True][f"{lvl}.group_idx"][0].cpu(), outs[False][f"{lvl}.group_idx"][0].cpu())
-        rel = (a - b).abs().max() / b.abs().max()
-        assert rel <= 1e-2, (lvl, rel)
+        scale = o.abs().max()
+        err_f, err_u = (a - o).abs().max() / scale, (b - o).abs().max() / scale
+        assert err_f <= 3e-2, (lvl, err_f)
+        assert err_f <= 1.5 * err_u + 5e-3, (lvl, err_f, err_u)

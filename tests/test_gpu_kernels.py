@@ -364,7 +364,7 @@ def test_attention_tcgen05(lib, lens):
     starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
     ds, dl = torch.as_tensor(starts).to(DEV), torch.as_tensor(np.asarray(lens, dtype=np.int32)).to(DEV)
     dq = qkv.to(DEV)
-    lib.call("pfpp_attention_tc", dq.data_ptr(), M, 3 * C, C, ds.data_ptr(), dl.data_ptr(), len(lens), max(lens), H,
+    lib.call("pfpp_attention_tc", dq.data_ptr(), M, 3 * C, C, ds.data_ptr(), dl.data_ptr(), len(lens), max(lens), H, 0,
              out.data_ptr(), C)
     torch.cuda.synchronize()
     o = out.cpu().float()
@@ -374,3 +374,25 @@ def test_attention_tcgen05(lib, lens):
         ref = torch.nn.functional.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1).reshape(n, C)
         err = (o[s:s + n] - ref).abs().max().item()
         assert err <= 2e-2, (n, err)
+
+
+@pytest.mark.parametrize("F", [1, 5, 13, 640])
+def test_attention_tcgen05_block_diagonal(lib, F):
+    """local attention: block-diagonal 25x25 blocks on 125-token tensor-core tiles vs per-block torch SDPA."""
+    H, D, L = 8, 64, 25
+    C = H * D
+    M = F * L
+    g = torch.Generator().manual_seed(F)
+    qkv = torch.randn(M, 3 * C, generator=g).to(torch.bfloat16)
+    out = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    n = (F + 4) // 5
+    starts = (np.arange(n) * 125).astype(np.int32)
+    lens = np.minimum(125, M - starts).astype(np.int32)
+    ds, dl = torch.as_tensor(starts).to(DEV), torch.as_tensor(lens).to(DEV)
+    dq = qkv.to(DEV)
+    lib.call("pfpp_attention_tc", dq.data_ptr(), M, 3 * C, C, ds.data_ptr(), dl.data_ptr(), n, 125, H, L, out.data_ptr(), C)
+    torch.cuda.synchronize()
+    o = out.cpu().float().view(F, L, C)
+    q, k, v = [t.reshape(F, L, H, D).transpose(1, 2) for t in qkv.float().chunk(3, -1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(F, L, C)
+    assert (o - ref).abs().max() <= 2e-2, (o - ref).abs().max()
