@@ -277,6 +277,210 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant for the wide denoiser projections (N >= 256): 128 x 256 output tiles, a 4-stage
+// TMA ring, the fp32 accumulator double-buffered in TMEM (2 x 256 columns) and dedicated epilogue
+// warps, so the epilogue of tile i (bias / GEGLU / residual, global stores) overlaps the main loop of
+// tile i+1.  One CTA per SM, static round-robin tile schedule with n fastest (the A row block is
+// re-used from L2 by consecutive tiles).
+//   warp 0 : TMA producer (lane 0)      warp 1 : MMA issuer (lane 0) + TMEM owner
+//   warps 2-5 : epilogue, warp w reads TMEM lane quarter (w % 4)
+// ------------------------------------------------------------------------------------------------
+constexpr int T2_BN = 256;
+constexpr int T2_STAGES = 4;
+constexpr uint32_t T2_A_BYTES = TC_BM * TC_BK * 2;
+constexpr uint32_t T2_B_BYTES = T2_BN * TC_BK * 2;
+constexpr uint32_t T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
+constexpr uint32_t T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t T2_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T2_BN >> 3) << 17) |
+                              ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int EPI, bool OUT_BF16>
+__global__ void __launch_bounds__(192)
+    gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const float* __restrict__ bias, const float* residual, int ldr, void* Cout, int ldc, int M,
+                         int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + T2_STAGES * T2_STAGE_BYTES;
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 8 * T2_STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * T2_STAGES;  // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;            // [2]
+  const uint32_t tmem_slot = bar_tempty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (N + T2_BN - 1) / T2_BN, tiles_m = (M + TC_BM - 1) / TC_BM;
+  const int num_tiles = tiles_n * tiles_m;
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * T2_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % T2_STAGES, round = it / T2_STAGES;
+          mbar_wait(bar_empty + 8 * s, (round & 1) ^ 1);
+          mbar_expect_tx(bar_full + 8 * s, T2_STAGE_BYTES);
+          const uint32_t sa = smem_base + s * T2_STAGE_BYTES;
+          tma_load_2d(sa, &map_a, bar_full + 8 * s, kb * TC_BK, m0);
+          tma_load_2d(sa + T2_A_BYTES, &map_b, bar_full + 8 * s, kb * TC_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1, use = lt >> 1;
+        mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + buf * T2_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % T2_STAGES, round = it / T2_STAGES;
+          mbar_wait(bar_full + 8 * s, round & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + s * T2_STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + T2_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, T2_IDESC, (kb | k) != 0);
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * T2_BN;
+      mbar_wait(bar_tfull + 8 * buf, use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + buf * T2_BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < T2_BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int nb = n0 + c * 32;
+        if (row < M && nb < N) {
+          if (EPI == PFPP_EPI_GEGLU) {
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int n = nb + j;
+              float val = __uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f);
+              float gate = __uint_as_float(v[j + 1]) + ((bias && n + 1 < N) ? bias[n + 1] : 0.f);
+              o[j >> 1] = val * gelu_erf(gate);
+            }
+            const size_t off = (size_t)row * ldc + (nb >> 1);
+            if (nb + 32 <= N && OUT_BF16 && (ldc % 8) == 0) {
+              __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + off;
+#pragma unroll
+              for (int j = 0; j < 16; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(cp + j) = pk;
+              }
+            } else {
+              for (int j = 0; j < 16; ++j) {
+                if (nb + 2 * j + 1 < N) {
+                  if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(Cout)[off + j] = __float2bfloat16_rn(o[j]);
+                  else reinterpret_cast<float*>(Cout)[off + j] = o[j];
+                }
+              }
+            }
+          } else {
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = nb + j;
+              o[j] = tc_act<EPI>(__uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f));
+            }
+            if (residual) {
+              const float* rp = residual + (size_t)row * ldr + nb;
+              if (nb + 32 <= N && (ldr % 4) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                  o[j] += r4.x, o[j + 1] += r4.y, o[j + 2] += r4.z, o[j + 3] += r4.w;
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (nb + j < N) o[j] += rp[j];
+              }
+            }
+            if (OUT_BF16) {
+              __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * ldc + nb;
+              if (nb + 32 <= N && (ldc % 8) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 pk;
+                  __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+                  __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                  *reinterpret_cast<uint4*>(cp + j) = pk;
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (nb + j < N) cp[j] = __float2bfloat16_rn(o[j]);
+              }
+            } else {
+              float* cp = reinterpret_cast<float*>(Cout) + (size_t)row * ldc + nb;
+              if (nb + 32 <= N && (ldc % 4) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (nb + j < N) cp[j] = o[j];
+              }
+            }
+          }
+        }
+      }
+      // this warp is done with the accumulator buffer: hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -302,6 +506,31 @@ int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PFPP_OK : PFPP_EINVAL;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int EPI>
+int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* residual, int ldr, void* C,
+               int ldc, int c_bf16, int M, int N, int K, cudaStream_t stream) {
+  const int tiles = pfpp_cdiv(N, T2_BN) * pfpp_cdiv(M, TC_BM);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  if (c_bf16) {
+    cudaFuncSetAttribute(gemm_bf16_tc2_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    gemm_bf16_tc2_kernel<EPI, true><<<grid, 192, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
+  } else {
+    cudaFuncSetAttribute(gemm_bf16_tc2_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    gemm_bf16_tc2_kernel<EPI, false><<<grid, 192, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
+  }
+  PFPP_RETURN_LAST();
 }
 
 template <int EPI>
@@ -332,8 +561,25 @@ extern "C" int pfpp_gemm_bf16(const void* A, int lda, const void* W, int ldw, co
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, lda, TC_BM);
   if (rc) return rc;
-  rc = make_map(&mb, W, N, K, ldw, TC_BN);
+  const bool wide = N >= T2_BN && M >= 2 * TC_BM;  // persistent 128x256 kernel for the wide projections
+  rc = make_map(&mb, W, N, K, ldw, wide ? T2_BN : TC_BN);
   if (rc) return rc;
+  if (wide) {
+    switch (epilogue) {
+      case PFPP_EPI_NONE:
+        return launch_tc2<PFPP_EPI_NONE>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      case PFPP_EPI_RELU:
+        return launch_tc2<PFPP_EPI_RELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      case PFPP_EPI_GELU:
+        return launch_tc2<PFPP_EPI_GELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      case PFPP_EPI_SILU:
+        return launch_tc2<PFPP_EPI_SILU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      case PFPP_EPI_GEGLU:
+        return launch_tc2<PFPP_EPI_GEGLU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      default:
+        return PFPP_EINVAL;
+    }
+  }
   switch (epilogue) {
     case PFPP_EPI_NONE:
       return launch_tc<PFPP_EPI_NONE>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);

@@ -161,7 +161,9 @@ def test_gemm_f32(lib, M, N, K, epi):
 
 @pytest.mark.parametrize("M,N,K,epi,out_bf16", [(300, 200, 136, 0, 0), (1000, 128, 64, 1, 1), (257, 512, 512, 2, 0),
                                                 (8192, 64, 8, 1, 1), (500, 4096, 512, 4, 1), (640, 1536, 512, 0, 1),
-                                                (100, 64, 512, 0, 0)])
+                                                (100, 64, 512, 0, 0), (16000, 1536, 512, 0, 1),
+                                                (16000, 512, 2048, 0, 0), (12345, 4096, 512, 4, 1),
+                                                (4000, 520, 512, 2, 0)])
 def test_gemm_bf16_tcgen05(lib, M, N, K, epi, out_bf16):
     """tcgen05/TMEM GEMM: bf16 operands, fp32 accumulation.  Reference = fp64 product of the SAME
     bf16-rounded operands, so the only error is accumulation order (+ bf16 output rounding)."""
