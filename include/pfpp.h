@@ -152,12 +152,20 @@ int pfpp_attention_tc(const void* qkv, long long M, int ld, int C, const int* se
 /* mean over L (denoiser_transformer.py:141-142). */
 int pfpp_mean_pool(const float* h, int F, int L, int C, int out_bf16, void* out, cudaStream_t stream);
 
-/* DDPMScheduler.step (diffusers 0.21.4; auto_aggl.py:149) + reference-part clamp (auto_aggl.py:150).
- * coef rows = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_x, sigma}; frag_coef selects a row per
- * fragment (NULL = row 0). x, noise, ref_pose are [slots,7]; only valid slots are touched. */
+/* DDPMScheduler.step (diffusers 0.21.4; auto_aggl.py:149) + reference-part clamp (auto_aggl.py:150) +
+ * trajectory record (auto_aggl.py:151, kept on the device).  coef rows = {sqrt(1-abar_t), sqrt(abar_t),
+ * c_x0, c_x, sigma}; frag_coef[f] = DDPM step index of fragment f (NULL = 0): selects the coef row, the noise
+ * row noise[step * noise_step_stride ...] and the history row x_hist[step * hist_step_stride ...] (x_hist may
+ * be NULL).  x, noise rows, ref_pose are [slots,7]; only valid slots are touched. */
 int pfpp_ddpm_step(const float* eps, int ld_eps, const int* frag_slot, const float* coef, const int* frag_coef,
-                   int add_noise, const float* noise, const unsigned char* ref, const float* ref_pose, int F,
-                   float* x, cudaStream_t stream);
+                   int add_noise, const float* noise, long long noise_step_stride, const unsigned char* ref,
+                   const float* ref_pose, int F, float* x, float* x_hist, long long hist_step_stride,
+                   cudaStream_t stream);
+
+/* Device-side step counter so that one captured CUDA graph serves every DDPM step of an outer iteration
+ * (replaces the host loop variable of auto_aggl.py:137): out[i] = *step ; *step += 1. */
+int pfpp_step_broadcast(const int* step, int* out, int n, cudaStream_t stream);
+int pfpp_step_advance(int* step, cudaStream_t stream);
 
 /* ---- verify / merge geometry ------------------------------------------------------------ */
 

@@ -39,7 +39,9 @@ SIGNATURES = {
     "pfpp_attention_varlen": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     "pfpp_attention_tc": [_P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P],
     "pfpp_mean_pool": [_P, _I, _I, _I, _I, _P, _P],
-    "pfpp_ddpm_step": [_P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P],
+    "pfpp_ddpm_step": [_P, _I, _P, _P, _P, _I, _P, _L, _P, _P, _I, _P, _P, _L, _P],
+    "pfpp_step_broadcast": [_P, _P, _I, _P],
+    "pfpp_step_advance": [_P, _P],
     "pfpp_pose_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P],
     "pfpp_edge_features": [_P, _P, _P, _P, _P, _P, _I, _I, _L, _P, _P],
     "pfpp_verifier_embed": [_P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P],

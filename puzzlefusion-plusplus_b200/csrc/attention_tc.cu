@@ -302,7 +302,7 @@ extern "C" int pfpp_attention_tc(const void* qkv, long long M, int ld, int C, co
          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return PFPP_EINVAL;
-  cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+  PFPP_ENSURE_SMEM(attention_tc_kernel, AT_SMEM_BYTES);
   dim3 grid(pfpp_cdiv(max_len, AT_BQ), heads, n_segments);
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)AT_D);
   attention_tc_kernel<<<grid, 128, AT_SMEM_BYTES, stream>>>(map, seg_start, seg_len, C, scale_log2e, block,

@@ -22,6 +22,17 @@
     if (!(cond)) return PFPP_EINVAL; \
   } while (0)
 
+// Raise a kernel's dynamic shared-memory limit once (and again only if a larger size is requested): keeps
+// cudaFuncSetAttribute out of the steady-state launch path and out of CUDA-graph capture.
+#define PFPP_ENSURE_SMEM(kernel, bytes)                                                              \
+  do {                                                                                               \
+    static int cur__ = 48 * 1024;                                                                    \
+    if ((int)(bytes) > cur__) {                                                                      \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));       \
+      cur__ = (int)(bytes);                                                                          \
+    }                                                                                                \
+  } while (0)
+
 static inline int pfpp_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Individually-rounded fp32 arithmetic.  The discrete stages (FPS argmax, ball-query radius

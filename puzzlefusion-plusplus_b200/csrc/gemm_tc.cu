@@ -15,6 +15,7 @@
 // one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "../../include/pfpp.h"
@@ -524,10 +525,10 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, 
   const int tiles = pfpp_cdiv(N, T2_BN) * pfpp_cdiv(M, TC_BM);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   if (c_bf16) {
-    cudaFuncSetAttribute(gemm_bf16_tc2_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    PFPP_ENSURE_SMEM((gemm_bf16_tc2_kernel<EPI, true>), T2_SMEM_BYTES);
     gemm_bf16_tc2_kernel<EPI, true><<<grid, 192, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
   } else {
-    cudaFuncSetAttribute(gemm_bf16_tc2_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    PFPP_ENSURE_SMEM((gemm_bf16_tc2_kernel<EPI, false>), T2_SMEM_BYTES);
     gemm_bf16_tc2_kernel<EPI, false><<<grid, 192, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
   }
   PFPP_RETURN_LAST();
@@ -538,10 +539,10 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, c
               int ldc, int c_bf16, int M, int N, int K, cudaStream_t stream) {
   dim3 grid(pfpp_cdiv(N, TC_BN), pfpp_cdiv(M, TC_BM));
   if (c_bf16) {
-    cudaFuncSetAttribute(gemm_bf16_tc_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    PFPP_ENSURE_SMEM((gemm_bf16_tc_kernel<EPI, true>), TC_SMEM_BYTES);
     gemm_bf16_tc_kernel<EPI, true><<<grid, 128, TC_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
   } else {
-    cudaFuncSetAttribute(gemm_bf16_tc_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    PFPP_ENSURE_SMEM((gemm_bf16_tc_kernel<EPI, false>), TC_SMEM_BYTES);
     gemm_bf16_tc_kernel<EPI, false><<<grid, 128, TC_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
   }
   PFPP_RETURN_LAST();
@@ -563,7 +564,11 @@ extern "C" int pfpp_gemm_bf16(const void* A, int lda, const void* W, int ldw, co
   if (rc) return rc;
   // persistent 128x256 kernel for the wide projections; the GEGLU epilogue (128 erf per row per tile) is
   // better spread over the 2 CTAs/SM of the 128x128 kernel (measured: 183 vs 254 us at M=16000, N=4096)
-  const bool wide = N >= T2_BN && M >= 2 * TC_BM && epilogue != PFPP_EPI_GEGLU;
+  static const int v2_mode = []() {
+    const char* e = getenv("PFPP_GEMM_V2");  // 0 = never, 1 = default policy, 2 = always (tuning knob)
+    return e ? atoi(e) : 1;
+  }();
+  const bool wide = N >= T2_BN && M >= 2 * TC_BM && v2_mode != 0 && (epilogue != PFPP_EPI_GEGLU || v2_mode == 2);
   rc = make_map(&mb, W, N, K, ldw, wide ? T2_BN : TC_BN);
   if (rc) return rc;
   if (wide) {

@@ -234,8 +234,7 @@ static int launch_fps(const float* src, const int* src_slot, int K, int N, int S
   } else if (N <= 2048) {
     PFPP_FPS_CASE(8);
   } else if (N <= 4096) {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(fps_kernel<16, ROTATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PFPP_ENSURE_SMEM((fps_kernel<16, ROTATE>), smem);
     PFPP_FPS_CASE(16);
   } else {
     return PFPP_EUNSUPPORTED;
@@ -331,8 +330,7 @@ extern "C" int pfpp_ball_query(const float* xyz, const float* new_xyz, int K, in
   if (K == 0) return PFPP_OK;
   size_t smem = (size_t)4 * N * sizeof(float);
   if (smem > 200 * 1024) return PFPP_EUNSUPPORTED;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PFPP_ENSURE_SMEM(ball_query_kernel, smem);
   dim3 grid(K, pfpp_cdiv(S, BQ_CENTROIDS_PER_CTA));
   ball_query_kernel<<<grid, BQ_WARPS * 32, smem, stream>>>(xyz, new_xyz, N, S, nsample, radius_sq, out_idx);
   PFPP_RETURN_LAST();
@@ -475,11 +473,11 @@ extern "C" int pfpp_vq(const void* z, int z_is_bf16, long long n_chunks, const f
   int grid = (int)((n_chunks + VQ_THREADS - 1) / VQ_THREADS);
   if (grid > 148 * 3) grid = 148 * 3;
   if (z_is_bf16) {
-    cudaFuncSetAttribute(vq_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PFPP_ENSURE_SMEM(vq_kernel<__nv_bfloat16>, smem);
     vq_kernel<__nv_bfloat16><<<grid, VQ_THREADS, smem, stream>>>((const __nv_bfloat16*)z, n_chunks, codebook, n_codes,
                                                                  out, codes);
   } else {
-    cudaFuncSetAttribute(vq_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PFPP_ENSURE_SMEM(vq_kernel<float>, smem);
     vq_kernel<float><<<grid, VQ_THREADS, smem, stream>>>((const float*)z, n_chunks, codebook, n_codes, out, codes);
   }
   PFPP_RETURN_LAST();

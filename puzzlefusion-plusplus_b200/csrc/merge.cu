@@ -151,9 +151,8 @@ extern "C" int pfpp_merge_filter(const float* pcs, int n_clouds, int n_points, i
   if (e != cudaSuccess) return (int)e;
   size_t smem_n = sizeof(float) * 3 * (size_t)n_points, smem_i = 2 * smem_n;
   if (smem_i > 200 * 1024) return PFPP_EUNSUPPORTED;
-  if (smem_n > 48 * 1024) cudaFuncSetAttribute(normals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n);
-  if (smem_i > 48 * 1024)
-    cudaFuncSetAttribute(intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i);
+  PFPP_ENSURE_SMEM(normals_kernel, smem_n);
+  PFPP_ENSURE_SMEM(intersect_kernel, smem_i);
   dim3 g1(pfpp_cdiv(n_points, 128), n_clouds);
   normals_kernel<<<g1, 128, smem_n, stream>>>(pcs, n_points, knn, normals);
   if (n_clouds > 1) {

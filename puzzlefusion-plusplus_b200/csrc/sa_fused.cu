@@ -402,7 +402,7 @@ int launch_sa(const SaParams& p, const void* w0, const void* w1, const void* w2,
   rc = weight_map(&m2, w2, C3, C2, C2);
   if (rc) return rc;
   auto kern = sa_fused_kernel<NS, D, C1, C2, C3, STAGES>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  PFPP_ENSURE_SMEM(kern, Cfg::SMEM);
   const long long tiles = (p.groups + Cfg::G - 1) / Cfg::G;
   kern<<<(unsigned)tiles, 160, Cfg::SMEM, stream>>>(m0, m1, m2, p);
   PFPP_RETURN_LAST();

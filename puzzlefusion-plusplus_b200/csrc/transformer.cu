@@ -317,28 +317,54 @@ extern "C" int pfpp_mean_pool(const float* h, int F, int L, int C, int out_bf16,
 // ---------------------------------------------------------------------------------------------
 __global__ void ddpm_step_kernel(const float* __restrict__ eps, int ld_eps, const int* __restrict__ frag_slot,
                                  const float* __restrict__ coef, const int* __restrict__ frag_coef, int add_noise,
-                                 const float* __restrict__ noise, const unsigned char* __restrict__ ref,
-                                 const float* __restrict__ ref_pose, int F, float* __restrict__ x) {
+                                 const float* __restrict__ noise, long long noise_step_stride,
+                                 const unsigned char* __restrict__ ref, const float* __restrict__ ref_pose, int F,
+                                 float* __restrict__ x, float* __restrict__ x_hist, long long hist_step_stride) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= F * 7) return;
   int f = i / 7, c = i - f * 7;
   int slot = frag_slot[f];
-  const float* cf = coef + 5 * (frag_coef ? frag_coef[f] : 0);
+  const int step = frag_coef ? frag_coef[f] : 0;
+  const float* cf = coef + 5 * step;
   float xv = x[(size_t)slot * 7 + c];
   float e = eps[(size_t)f * ld_eps + c];
   float x0 = fdiv(fsub(xv, fmul(cf[0], e)), cf[1]);
   float prev = fadd(fmul(cf[2], x0), fmul(cf[3], xv));
-  if (add_noise) prev = fadd(prev, fmul(cf[4], noise[(size_t)slot * 7 + c]));
+  if (add_noise) prev = fadd(prev, fmul(cf[4], noise[(size_t)step * noise_step_stride + (size_t)slot * 7 + c]));
   if (ref[slot]) prev = ref_pose[(size_t)slot * 7 + c];
   x[(size_t)slot * 7 + c] = prev;
+  if (x_hist) x_hist[(size_t)step * hist_step_stride + (size_t)slot * 7 + c] = prev;
 }
 
 extern "C" int pfpp_ddpm_step(const float* eps, int ld_eps, const int* frag_slot, const float* coef,
-                              const int* frag_coef, int add_noise, const float* noise, const unsigned char* ref,
-                              const float* ref_pose, int F, float* x, cudaStream_t stream) {
+                              const int* frag_coef, int add_noise, const float* noise, long long noise_step_stride,
+                              const unsigned char* ref, const float* ref_pose, int F, float* x, float* x_hist,
+                              long long hist_step_stride, cudaStream_t stream) {
   PFPP_CHECK_ARG(eps && frag_slot && coef && ref && ref_pose && x && (!add_noise || noise));
   if (F == 0) return PFPP_OK;
   ddpm_step_kernel<<<pfpp_cdiv(F * 7, 128), 128, 0, stream>>>(eps, ld_eps, frag_slot, coef, frag_coef, add_noise, noise,
-                                                             ref, ref_pose, F, x);
+                                                             noise_step_stride, ref, ref_pose, F, x, x_hist,
+                                                             hist_step_stride);
+  PFPP_RETURN_LAST();
+}
+
+// Device-side DDPM step counter: lets one captured CUDA graph serve all T steps of an outer iteration.
+// pfpp_step_broadcast: out[i] = *step (per-fragment AdaLN row / coefficient row / noise row index);
+// pfpp_step_advance:   *step += 1.
+__global__ void step_broadcast_kernel(const int* __restrict__ step, int* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = *step;
+}
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+
+extern "C" int pfpp_step_broadcast(const int* step, int* out, int n, cudaStream_t stream) {
+  PFPP_CHECK_ARG(step && out && n >= 0);
+  if (n == 0) return PFPP_OK;
+  step_broadcast_kernel<<<pfpp_cdiv(n, 256), 256, 0, stream>>>(step, out, n);
+  PFPP_RETURN_LAST();
+}
+extern "C" int pfpp_step_advance(int* step, cudaStream_t stream) {
+  PFPP_CHECK_ARG(step);
+  step_advance_kernel<<<1, 1, 0, stream>>>(step);
   PFPP_RETURN_LAST();
 }

@@ -72,8 +72,7 @@ extern "C" int pfpp_edge_features(const float* pts, const int* pair_src, const i
   PFPP_CHECK_ARG(pts && pair_src && pair_tgt && edge_start && edge_len && edge_row && max_pairs > 0);
   size_t smem = sizeof(float) * 6 * (size_t)max_pairs;
   if (smem > 200 * 1024) return PFPP_EUNSUPPORTED;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(edge_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PFPP_ENSURE_SMEM(edge_features_kernel, smem);
   edge_features_kernel<<<n_edges, EDGE_THREADS, smem, stream>>>(pts, pair_src, pair_tgt, edge_start, edge_len, edge_row,
                                                                  max_pairs, feat);
   PFPP_RETURN_LAST();

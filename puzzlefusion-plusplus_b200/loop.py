@@ -25,7 +25,9 @@ from .pose_utils import affine, compose_params, compose_params_steps, quat_to_ma
 
 class GlobalTorchNoise:
     """The reference's RNG protocol (App. C.1): draws from torch's global generator of the device, in
-    the same order and shapes -- randn([B,P,7]) once, then once per step with t > 0, rand(1) per merge."""
+    the same order and shapes -- randn([B,P,7]) once, then once per step with t > 0, rand(1) per merge.
+    (Nothing else consumes the generator inside the inner loop, so the T-1 per-step draws of an outer
+    iteration are made up front, in order.)"""
 
     def __init__(self, device):
         self.device = device
@@ -33,8 +35,10 @@ class GlobalTorchNoise:
     def initial(self, B, P):
         return torch.randn((B, P, 7), device=self.device)
 
-    def step(self, B, P):
-        return torch.randn((B, P, 7), device=self.device)
+    def iteration_noise(self, B, P, timesteps):
+        rows = [torch.randn((B, P, 7), device=self.device) if t > 0 else torch.zeros((B, P, 7), device=self.device)
+                for t in timesteps]
+        return torch.stack(rows).reshape(len(timesteps), B * P, 7).contiguous()
 
     def fps_start(self, b, M):
         return int((torch.rand(1, device=self.device) * float(M)).to(torch.int64))
@@ -44,14 +48,17 @@ class ReplayNoise:
     """Pre-drawn noise (parity tests: the oracle and this loop consume identical tensors)."""
 
     def __init__(self, normals, uniforms, device):
+        self.device = device
         self.normals = [n.to(device) for n in normals]
         self.uniforms = list(uniforms)
 
     def initial(self, B, P):
         return self.normals.pop(0).reshape(B, P, 7).clone()
 
-    def step(self, B, P):
-        return self.normals.pop(0).reshape(B, P, 7).clone()
+    def iteration_noise(self, B, P, timesteps):
+        rows = [self.normals.pop(0).reshape(B, P, 7) if t > 0 else torch.zeros((B, P, 7), device=self.device)
+                for t in timesteps]
+        return torch.stack(rows).reshape(len(timesteps), B * P, 7).contiguous()
 
     def fps_start(self, b, M):
         u = self.uniforms.pop(0)
@@ -65,20 +72,14 @@ class PerObjectNoise:
     def __init__(self, device, seeds, T):
         self.device, self.T = device, T
         self.gens = [torch.Generator(device=device).manual_seed(int(s)) for s in seeds]
-        self.cur = None
-        self.k = 0
 
     def initial(self, B, P):
         return torch.cat([torch.randn((1, P, 7), device=self.device, generator=g) for g in self.gens], 0)
 
-    def begin_iteration(self, B, P):
-        self.cur = torch.stack([torch.randn((self.T, P, 7), device=self.device, generator=g) for g in self.gens], 1)
-        self.k = 0
-
-    def step(self, B, P):
-        out = self.cur[self.k]
-        self.k += 1
-        return out
+    def iteration_noise(self, B, P, timesteps):
+        T = len(timesteps)
+        cur = torch.stack([torch.randn((T, P, 7), device=self.device, generator=g) for g in self.gens], 1)
+        return cur.reshape(T, B * P, 7).contiguous()
 
     def fps_start(self, b, M):
         return int((torch.rand(1, device=self.device, generator=self.gens[b]) * float(M)).to(torch.int64))
@@ -171,81 +172,187 @@ def _seg_tensors(engine, frag_counts):
     return (loc_start, loc_len), (glo_start, glo_len), int(max(frag_counts)) * L
 
 
+class BatchRunner:
+    """One batch advanced through the loop in three phases per outer iteration so that several runners
+    (each on its own CUDA stream) can be interleaved by one host thread:
+        begin_iteration() -> step() x T -> end_iteration()
+    The T DDPM steps of an iteration share one launch sequence whose only step-dependent inputs (AdaLN
+    row, scheduler coefficients, noise row, history row) are indexed by a DEVICE-side step counter; with
+    ``use_graph`` the sequence is captured once per iteration (after an eager first step that also sizes
+    the workspaces) and replayed as a CUDA graph."""
+
+    def __init__(self, engine, objects=None, max_iters=1, threshold=0.9, noise=None, merge=True, record=None,
+                 trajectory=True, state=None, verify_last=False, use_graph=True):
+        self.e, self.max_iters, self.threshold, self.merge = engine, max_iters, threshold, merge
+        self.record, self.trajectory, self.verify_last = record, trajectory, verify_last
+        self.use_graph = use_graph and record is None
+        dev, P = engine.device, engine.P
+        self.st = st = state if state is not None else BatchState(engine, objects)
+        B = st.B
+        self.noise = noise or GlobalTorchNoise(dev)
+        x = self.noise.initial(B, P).to(torch.float32)
+        ref_mask = torch.as_tensor(st.ref).to(dev)
+        ref_pose = torch.zeros_like(st.gt)
+        ref_pose[ref_mask] = st.gt[ref_mask]
+        x[ref_mask] = ref_pose[ref_mask]
+        self.x = x.reshape(B * P, 7).contiguous()
+        self.ref_pose = ref_pose.reshape(B * P, 7).contiguous()
+        self.ref_dev = ref_mask.reshape(B * P).to(torch.uint8).contiguous()
+        self.x_hist = torch.empty(max_iters * engine.T, B * P, 7, device=dev)
+        self.traj = [[] for _ in range(B)]
+        self.iters = [0] * B
+        self.timesteps = [int(t) for t in engine.sched.timesteps]
+        self.step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.it = 0
+        self.graph = None
+        self._cap_stream = None
+        self.finished = False
+
+    # -- phase 1 ---------------------------------------------------------------------------------
+    def begin_iteration(self):
+        st, e = self.st, self.e
+        if self.finished or self.it >= self.max_iters:
+            self.finished = True
+            return False
+        self.active = [b for b in range(st.B) if not st.done[b]]
+        if not self.active:
+            self.finished = True
+            return False
+        P = e.P
+        slots, counts = [], []
+        for b in self.active:
+            s = [b * P + p for p in range(P) if st.valid[b, p]]
+            slots += s
+            counts.append(len(s))
+        self.frag_slot = torch.as_tensor(np.asarray(slots, dtype=np.int32)).to(e.device)
+        self.F = len(slots)
+        self.frag_step = torch.zeros(self.F, dtype=torch.int32, device=e.device)
+        self.seg_local, self.seg_global, self.max_global = _seg_tensors(e, counts)
+        self.noise_all = self.noise.iteration_noise(st.B, P, self.timesteps)
+        self.step_ctr.zero_()
+        self.si = 0
+        self.graph = None
+        return True
+
+    def _launch_step(self):
+        st, e = self.st, self.e
+        call("pfpp_step_broadcast", self.step_ctr.data_ptr(), self.frag_step.data_ptr(), self.F)
+        latent, xyz = e.encode(st.part_pcs, self.frag_slot, self.x, st.N)
+        eps = e.denoise_eps(self.x, st.scale, self.ref_dev, self.frag_slot, self.frag_step, latent, xyz, self.seg_local,
+                            self.seg_global, self.max_global)
+        hist = self.x_hist[self.it * e.T:]
+        call("pfpp_ddpm_step", eps.data_ptr(), 8, self.frag_slot.data_ptr(), e.coef.data_ptr(), self.frag_step.data_ptr(),
+             1, self.noise_all.data_ptr(), self.noise_all.stride(0), self.ref_dev.data_ptr(), self.ref_pose.data_ptr(),
+             self.F, self.x.data_ptr(), hist.data_ptr(), hist.stride(0))
+        call("pfpp_step_advance", self.step_ctr.data_ptr())
+        return eps
+
+    # -- phase 2 ---------------------------------------------------------------------------------
+    def step(self):
+        """Enqueue DDPM step `self.si` of the current outer iteration on the current stream."""
+        e = self.e
+        if self.graph is not None:
+            self.graph.replay()
+        elif self.use_graph and self.si == 1 and e.T > 2:
+            # capture on a private side stream (no host synchronisation, no allocator flush), replay on the
+            # runner's stream
+            g = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream()
+            if self._cap_stream is None:
+                self._cap_stream = torch.cuda.Stream(device=e.device)
+            self._cap_stream.wait_stream(cur)
+            with torch.cuda.stream(self._cap_stream):
+                g.capture_begin()
+                try:
+                    self._launch_step()
+                finally:
+                    g.capture_end()
+            cur.wait_stream(self._cap_stream)
+            self.graph = g
+            g.replay()
+        else:
+            eps = self._launch_step()
+            if self.record is not None:
+                self.record.append({"t": self.timesteps[self.si], "eps": eps[:, :7].clone(), "x": self.x.clone(),
+                                    "frag_slot": self.frag_slot.clone()})
+        self.si += 1
+
+    # -- phase 3 ---------------------------------------------------------------------------------
+    def end_iteration(self):
+        st, e = self.st, self.e
+        B, P, T = st.B, e.P, e.T
+        for b in self.active:
+            self.iters[b] += 1
+        x_host = self.x.cpu().reshape(B, P, 7)  # the one D2H read of this outer iteration
+        if self.trajectory:
+            xh = self.x_hist[self.it * T:(self.it + 1) * T].cpu().reshape(T, B, P, 7)
+            for b in self.active:
+                self.traj[b].append(compose_params_steps(xh[:, b], st.pivot[b], st.init_pose[b]))
+        last = self.it + 1 == self.max_iters
+        if last and not self.verify_last:
+            self.finished = True
+            return
+        # verify_last: BASELINE config 2 = one denoise pass + one verifier pass (no merge, no second pass)
+        _verify_and_merge(e, st, self.active, self.x, x_host, self.ref_dev, self.ref_pose, self.threshold, self.noise,
+                          self.merge and not last, self.record)
+        self.it += 1
+        if last:
+            self.finished = True
+
+    def result(self):
+        st, e = self.st, self.e
+        B, P = st.B, e.P
+        x_host = self.x.cpu().reshape(B, P, 7)
+        pred_t = torch.zeros(B, P, 3)
+        pred_r = torch.zeros(B, P, 4)
+        for b in range(B):
+            tr, qr = compose_params(x_host[b], st.pivot[b], st.init_pose[b])
+            pred_t[b, :st.num_parts[b]] = tr
+            pred_r[b, :st.num_parts[b]] = qr
+        return {"x": x_host, "pred_trans": pred_t, "pred_rots": pred_r,
+                "trajectory": [torch.cat(t) if t else torch.zeros(0) for t in self.traj], "iters": self.iters,
+                "pivots": st.pivot, "ref_part": torch.as_tensor(st.ref), "part_valids": torch.as_tensor(st.valid)}
+
+
+def run_interleaved(runners, streams=None):
+    """Advance several BatchRunners in lock-step from one host thread, runner i on streams[i]: the
+    latency-bound geometry kernels of one batch overlap the tensor-core kernels of another."""
+    cur = torch.cuda.current_stream()
+    streams = streams or [cur] * len(runners)
+    for s_ in streams:
+        if s_ is not cur:
+            s_.wait_stream(cur)
+    while True:
+        live = []
+        for r, s_ in zip(runners, streams):
+            with torch.cuda.stream(s_):
+                if r.begin_iteration():
+                    live.append((r, s_))
+        if not live:
+            break
+        for _ in range(runners[0].e.T):
+            for r, s_ in live:
+                with torch.cuda.stream(s_):
+                    r.step()
+        for r, s_ in live:
+            with torch.cuda.stream(s_):
+                r.end_iteration()
+    for s_ in streams:
+        if s_ is not cur:
+            cur.wait_stream(s_)
+    return [r.result() for r in runners]
+
+
 def run_batch(engine, objects, max_iters, threshold=0.9, noise=None, merge=True, record=None, trajectory=True,
-              state=None, verify_last=False):
+              state=None, verify_last=False, use_graph=True):
     """Run the full loop on a list of per-object dicts (no batch dim).
 
     ``state`` may carry a pre-built BatchState (inputs already resident in HBM; a BatchState is
     consumed by the run).  Returns dict(x [B,P,7], pred_trans [B,P,3], pred_rots [B,P,4], trajectory
     list per object ([T_total, n_nodes, 7]), iters [B])."""
-    dev, P, T = engine.device, engine.P, engine.T
-    st = state if state is not None else BatchState(engine, objects)
-    B, N = st.B, st.N
-    noise = noise or GlobalTorchNoise(dev)
-    x = noise.initial(B, P).to(torch.float32)
-    ref_mask = torch.as_tensor(st.ref).to(dev)
-    ref_pose = torch.zeros_like(st.gt)
-    ref_pose[ref_mask] = st.gt[ref_mask]
-    x[ref_mask] = ref_pose[ref_mask]
-    x = x.reshape(B * P, 7).contiguous()
-    ref_pose = ref_pose.reshape(B * P, 7).contiguous()
-    ref_dev = ref_mask.reshape(B * P).to(torch.uint8).contiguous()
-    x_hist = torch.empty(max_iters * T, B * P, 7, device=dev)
-    traj = [[] for _ in range(B)]
-    iters = [0] * B
-    timesteps = [int(t) for t in engine.sched.timesteps]
-
-    for it in range(max_iters):
-        active = [b for b in range(B) if not st.done[b]]
-        if not active:
-            break
-        slots, counts = [], []
-        for b in active:
-            s = [b * P + p for p in range(P) if st.valid[b, p]]
-            slots += s
-            counts.append(len(s))
-        frag_slot = torch.as_tensor(np.asarray(slots, dtype=np.int32)).to(dev)
-        F = len(slots)
-        frag_tidx = torch.zeros(F, dtype=torch.int32, device=dev)
-        seg_local, seg_global, max_global = _seg_tensors(engine, counts)
-        if hasattr(noise, "begin_iteration"):
-            noise.begin_iteration(B, P)
-        for si, t in enumerate(timesteps):
-            frag_tidx.fill_(si)
-            latent, xyz = engine.encode(st.part_pcs, frag_slot, x, N)
-            eps = engine.denoise_eps(x, st.scale, ref_dev, frag_slot, frag_tidx, latent, xyz, seg_local, seg_global,
-                                     max_global)
-            nz = noise.step(B, P).reshape(B * P, 7).contiguous() if t > 0 else x
-            call("pfpp_ddpm_step", eps.data_ptr(), 8, frag_slot.data_ptr(), engine.coef.data_ptr() + 20 * si, None, 1,
-                 nz.data_ptr(), ref_dev.data_ptr(), ref_pose.data_ptr(), F, x.data_ptr())
-            x_hist[it * T + si].copy_(x)
-            if record is not None:
-                record.append({"t": t, "eps": eps[:, :7].clone(), "x": x.clone(), "frag_slot": frag_slot.clone()})
-        for b in active:
-            iters[b] += 1
-        x_host = x.cpu().reshape(B, P, 7)  # the one D2H read of this outer iteration
-        xh = x_hist[it * T:(it + 1) * T].cpu().reshape(T, B, P, 7)
-        if trajectory:
-            for b in active:
-                traj[b].append(compose_params_steps(xh[:, b], st.pivot[b], st.init_pose[b]))
-        if it + 1 == max_iters and not verify_last:
-            break
-        # verify_last: BASELINE config 2 = one denoise pass + one verifier pass (no merge, no second pass)
-        _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshold, noise,
-                          merge and it + 1 < max_iters, record)
-        if it + 1 == max_iters:
-            break
-
-    x_host = x.cpu().reshape(B, P, 7)
-    pred_t = torch.zeros(B, P, 3)
-    pred_r = torch.zeros(B, P, 4)
-    for b in range(B):
-        tr, qr = compose_params(x_host[b], st.pivot[b], st.init_pose[b])
-        pred_t[b, :st.num_parts[b]] = tr
-        pred_r[b, :st.num_parts[b]] = qr
-    return {"x": x_host, "pred_trans": pred_t, "pred_rots": pred_r,
-            "trajectory": [torch.cat(t) if t else torch.zeros(0) for t in traj], "iters": iters,
-            "pivots": st.pivot, "ref_part": torch.as_tensor(st.ref), "part_valids": torch.as_tensor(st.valid)}
+    r = BatchRunner(engine, objects, max_iters, threshold, noise, merge, record, trajectory, state, verify_last,
+                    use_graph)
+    return run_interleaved([r])[0]
 
 
 def _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshold, noise, merge, record):

@@ -76,6 +76,6 @@ class PiecewiseScheduler:
                             dtype=sample.dtype).reshape(-1, 7) if t > 0 else torch.zeros_like(flat)
         slot = torch.arange(n, device=sample.device, dtype=torch.int32)
         ref = torch.zeros(n, device=sample.device, dtype=torch.uint8)
-        _lib.call("pfpp_ddpm_step", eps.data_ptr(), 7, slot.data_ptr(), coef.data_ptr(), None, 1, noise.data_ptr(),
-                  ref.data_ptr(), flat.data_ptr(), n, flat.data_ptr())
+        _lib.call("pfpp_ddpm_step", eps.data_ptr(), 7, slot.data_ptr(), coef.data_ptr(), None, 1, noise.data_ptr(), 0,
+                  ref.data_ptr(), flat.data_ptr(), n, flat.data_ptr(), None, 0)
         return SchedulerOutput(flat.reshape(sample.shape))

@@ -80,9 +80,6 @@ def test_test_step_runs_like_the_reference(ckpt, tmp_path, precision):
     tot = m.on_test_epoch_end()
     assert len(tot) == 4 and all(torch.isfinite(t) for t in tot) and m.acc_list == []
     objs = [synthetic.make_object(900 + i, num_parts=n) for i, n in enumerate((6, 11))]
-    batch = {k: (torch.stack([o[k] for o in objs]) if torch.is_tensor(objs[0][k]) else [o[k] for o in objs])
-             for k in objs[0] if k != "correspondences"}
-    batch["num_parts"] = torch.tensor([o["num_parts"] for o in objs])
     m2 = _model(ckpt, tmp_path, precision, max_iters=1)
     from puzzlefusion_plusplus_b200.loop import GlobalTorchNoise, run_batch
     res = run_batch(m2.engine, objs, max_iters=1, noise=GlobalTorchNoise(m2.engine.device))

@@ -265,8 +265,8 @@ def test_ddpm_step_bit_exact(lib):
     for t, key in ((950, "step_prev_t950"), (0, "step_prev_t0")):
         xx = x.clone()
         coef = s.coefficients(t).to(DEV)
-        lib.call("pfpp_ddpm_step", eps.data_ptr(), 8, slot.data_ptr(), coef.data_ptr(), None, 1, noise.data_ptr(),
-                 ref.data_ptr(), xx.data_ptr(), 20, xx.data_ptr())
+        lib.call("pfpp_ddpm_step", eps.data_ptr(), 8, slot.data_ptr(), coef.data_ptr(), None, 1, noise.data_ptr(), 0,
+                 ref.data_ptr(), xx.data_ptr(), 20, xx.data_ptr(), None, 0)
         assert torch.equal(xx.cpu(), g[key][0]), (xx.cpu() - g[key][0]).abs().max()
 
 
