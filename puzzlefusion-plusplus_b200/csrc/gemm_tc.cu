@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(128)
 // tile i+1.  One CTA per SM, static round-robin tile schedule with n fastest (the A row block is
 // re-used from L2 by consecutive tiles).
 //   warp 0 : TMA producer (lane 0)      warp 1 : MMA issuer (lane 0) + TMEM owner
-//   warps 2-5 : epilogue, warp w reads TMEM lane quarter (w % 4)
+//   warps 2-9 : epilogue, warp w reads TMEM lane quarter (w % 4); warps 2-5 take columns 0-127 of the
+//               tile, warps 6-9 columns 128-255 (the epilogue, not the main loop, bounds these shapes)
 // ------------------------------------------------------------------------------------------------
 constexpr int T2_BN = 256;
 constexpr int T2_STAGES = 4;
@@ -300,8 +301,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+constexpr int T2_THREADS = 64 + 256;
+
 template <int EPI, bool OUT_BF16>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(T2_THREADS)
     gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const float* __restrict__ bias, const float* residual, int ldr, void* Cout, int ldc, int M,
                          int N, int K) {
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(192)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 4);  // one arrival per epilogue warp
+      mbar_init(bar_tempty + 8 * b, 8);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -375,7 +378,8 @@ __global__ void __launch_bounds__(192)
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int chalf = (warp - 2) >> 2;      // which 128-column half of the tile this warp drains
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       const uint32_t buf = lt & 1, use = lt >> 1;
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(192)
       const int row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + buf * T2_BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < T2_BN / 32; ++c) {
+      for (int c = chalf * (T2_BN / 64); c < (chalf + 1) * (T2_BN / 64); ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -526,10 +530,10 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, 
   const int grid = tiles < sm_count() ? tiles : sm_count();
   if (c_bf16) {
     PFPP_ENSURE_SMEM((gemm_bf16_tc2_kernel<EPI, true>), T2_SMEM_BYTES);
-    gemm_bf16_tc2_kernel<EPI, true><<<grid, 192, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
+    gemm_bf16_tc2_kernel<EPI, true><<<grid, T2_THREADS, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
   } else {
     PFPP_ENSURE_SMEM((gemm_bf16_tc2_kernel<EPI, false>), T2_SMEM_BYTES);
-    gemm_bf16_tc2_kernel<EPI, false><<<grid, 192, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
+    gemm_bf16_tc2_kernel<EPI, false><<<grid, T2_THREADS, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
   }
   PFPP_RETURN_LAST();
 }

@@ -3,15 +3,16 @@
 // (utils/pn2_utils.py:139-148 and :209-214).  Activations never leave the SM: the gathered rows and
 // the two hidden layers live in shared memory as bf16 UMMA operand tiles, accumulators in TMEM.
 //
-// One CTA owns 128 grouped rows (4 groups of 32 samples, or 2 groups of 64).
+// One CTA owns SUB x 128 grouped rows (SUB = 2 for levels 2/3: both sub-tiles consume every weight stage, which
+// halves the L2 weight traffic that bounds the kernel; 128 rows = 4 groups of 32 samples or 2 groups of 64).
 //   layers 0,1  D[rows x C] = X[rows x K] . W^T   rows on the M axis; the epilogue thread owns one row,
 //               adds the bias, applies ReLU and writes the bf16 row into the next layer's K-major
 //               SWIZZLE_128B operand tile (16-byte stores).
 //   layer 2     D[C x rows] = W[C x K] . X^T      channels on the M axis (128 per MMA block); the
 //               epilogue thread owns one channel, so the max over a group's nsample rows is a plain
 //               register reduction over TMEM columns; bias + ReLU commute with the max.
-// CTA = 5 warps: warps 0-3 gather / issue MMAs (lane 0 of warp 1) / run the epilogues, warp 4 is the TMA
-// weight producer.  Weight tiles [128 x 64] stream through a ring (full/empty mbarriers) that runs ahead across
+// CTA = 4*SUB compute warps (gather, MMA issue by lane 0 of warp 1, epilogues; warp w works on sub-tile w/4 and
+// TMEM lane quarter w%4) + one TMA weight-producer warp.  Weight tiles [128 x 64] stream through a ring (full/empty mbarriers) that runs ahead across
 // layer boundaries; X tiles are written by the CTA's own threads (generic proxy) and published to the
 // tensor core with fence.proxy.async.
 //
@@ -111,37 +112,44 @@ struct SaParams {
   long long groups;        // K * S
 };
 
-template <int NS, int D, int C1, int C2, int C3, int STAGES>
+template <int NS, int D, int C1, int C2, int C3, int STAGES, int SUB>
 struct SaCfg {
+  static constexpr int ROWS = 128 * SUB;                    // grouped rows per CTA (SUB sub-tiles of 128)
+  static constexpr int THREADS = ROWS + 32;                 // compute warps + one TMA producer warp
   static constexpr int K0 = D;                              // layer-0 tensor-core K (feature columns only)
   static constexpr int P0 = D / 64;                         // panels of X0 (0 for the first level)
   static constexpr int P1 = (C1 + 63) / 64, P2 = (C2 + 63) / 64;
   static constexpr int NB1 = (C1 + 127) / 128, NB2 = (C2 + 127) / 128, MB3 = C3 / 128;
   static constexpr int X_PANELS = (P0 > P1 ? (P0 > P2 ? P0 : P2) : (P1 > P2 ? P1 : P2));
-  static constexpr uint32_t OFF_X = 0;                      // X0 -> X1 -> X2 in place
-  static constexpr uint32_t OFF_W = X_PANELS * SF_TILE;
+  static constexpr uint32_t X_BYTES = X_PANELS * SF_TILE;   // one sub-tile's operand buffer (X0 -> X1 -> X2 in place)
+  static constexpr uint32_t OFF_X = 0;
+  static constexpr uint32_t OFF_W = SUB * X_BYTES;
   static constexpr uint32_t OFF_BAR = OFF_W + STAGES * SF_TILE;
-  static constexpr uint32_t OFF_ROWS = OFF_BAR + 128;        // [128] int64 gather offsets
-  static constexpr uint32_t OFF_CONST = OFF_ROWS + 1024;     // wxyz [C1][4] | b0 [C1] | b1 [C2] | b2 [C3]  (fp32)
+  static constexpr uint32_t OFF_ROWS = OFF_BAR + 128;        // [ROWS] int64 gather offsets
+  static constexpr uint32_t OFF_CONST = OFF_ROWS + 8 * ROWS; // wxyz [C1][4] | b0 [C1] | b1 [C2] | b2 [C3]  (fp32)
   static constexpr uint32_t CONST_BYTES = (C1 * 5 + C2 + C3) * 4;
   static constexpr uint32_t SMEM = OFF_CONST + CONST_BYTES + 1024 /*align slack*/;
-  static constexpr int TMEM_COLS = (C1 > 128 || C2 > 128) ? 256 : 128;
-  static constexpr int G = 128 / NS;                        // groups per CTA
+  static constexpr int CW = (NB1 > NB2 ? NB1 : NB2) * 128;  // TMEM columns per sub-tile in layers 0/1
+  static constexpr int TMEM_NEED = SUB * (CW > 128 ? CW : 128);
+  static constexpr int TMEM_COLS = TMEM_NEED > 256 ? 512 : (TMEM_NEED > 128 ? 256 : 128);
+  static constexpr int GS = 128 / NS;                       // groups per sub-tile
+  static constexpr int G = GS * SUB;                        // groups per CTA
 };
 
-template <int NS, int D, int C1, int C2, int C3, int STAGES>
-__global__ void __launch_bounds__(160)
+template <int NS, int D, int C1, int C2, int C3, int STAGES, int SUB>
+__global__ void __launch_bounds__(128 * SUB + 32)
     sa_fused_kernel(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
                     const __grid_constant__ CUtensorMap map_w2, const SaParams p) {
-  using Cfg = SaCfg<NS, D, C1, C2, C3, STAGES>;
+  using Cfg = SaCfg<NS, D, C1, C2, C3, STAGES, SUB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar_full = base + Cfg::OFF_BAR;             // [STAGES]
   const uint32_t bar_empty = bar_full + 8 * STAGES;          // [STAGES]
-  const uint32_t bar_acc = bar_empty + 8 * STAGES;           // accumulator of the current layer complete
+  const uint32_t bar_acc = bar_empty + 8 * STAGES;           // accumulators of the current layer complete
   const uint32_t tmem_slot = bar_acc + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = warp >> 2, wq = warp & 3;                  // sub-tile and TMEM lane quarter of a compute warp
   const long long g0 = (long long)blockIdx.x * Cfg::G;
 
   if (threadIdx.x == 0) {
@@ -162,8 +170,8 @@ __global__ void __launch_bounds__(160)
   const uint32_t tmem = *reinterpret_cast<uint32_t*>(bp + Cfg::OFF_BAR + 16 * STAGES + 8);
 
   // ---------------- weight producer: one elected thread, runs ahead over all three layers ----------
-  // stage order == consumption order of the MMA issuer below
-  if (warp == 4) {
+  // stage order == consumption order of the MMA issuer below; every stage feeds all SUB sub-tiles
+  if (warp == 4 * SUB) {
     if (lane != 0) return;
     int it = 0;
     auto push = [&](const CUtensorMap* m, int kcol, int row) {
@@ -184,16 +192,16 @@ __global__ void __launch_bounds__(160)
     return;  // the ring drains on its own; shared memory stays live until the compute warps exit
   }
 
+#define SA_BAR() asm volatile("bar.sync 1, %0;" ::"n"(Cfg::ROWS) : "memory")
+
   float d3[3] = {0.f, 0.f, 0.f};  // this thread's row: xyz[idx] - centroid (fp32, used by the layer-0 epilogue)
   // ---------------- gather: X0[row] = feats[idx] (bf16, swizzled) ----------
-  // phase 1: thread = row -> neighbour index, xyz offset columns; phase 2: all 128 threads stream the
-  // feature rows as 16-byte chunks (consecutive threads = consecutive chunks of a row), 8 loads in flight.
+  // phase 1: thread = row -> neighbour index, xyz offset; phase 2: all threads stream the feature rows as
+  // 16-byte chunks (consecutive threads = consecutive chunks of a row), 8 loads in flight per thread.
   {
-    uint8_t* xa = bp + Cfg::OFF_X;
-    long long* src_row = reinterpret_cast<long long*>(bp + Cfg::OFF_ROWS);  // [128] element offsets, -1 = padding
-    (void)xa;
+    long long* src_row = reinterpret_cast<long long*>(bp + Cfg::OFF_ROWS);  // element offsets, -1 = padding
     {
-      const int r = threadIdx.x;
+      const int r = threadIdx.x;  // 0 .. ROWS-1
       const long long g = g0 + r / NS;
       const bool valid = g < p.groups;
       long long off = -1;
@@ -209,41 +217,44 @@ __global__ void __launch_bounds__(160)
     }
     {  // per-channel constants -> shared memory (broadcast LDS in the epilogues instead of dependent LDGs)
       float* cst = reinterpret_cast<float*>(bp + Cfg::OFF_CONST);
-      for (int i = threadIdx.x; i < C1 * 4; i += 128) cst[i] = p.wxyz[i];
-      for (int i = threadIdx.x; i < C1; i += 128) cst[C1 * 4 + i] = p.b0[i];
-      for (int i = threadIdx.x; i < C2; i += 128) cst[C1 * 5 + i] = p.b1[i];
-      for (int i = threadIdx.x; i < C3; i += 128) cst[C1 * 5 + C2 + i] = p.b2[i];
+      for (int i = threadIdx.x; i < C1 * 4; i += Cfg::ROWS) cst[i] = p.wxyz[i];
+      for (int i = threadIdx.x; i < C1; i += Cfg::ROWS) cst[C1 * 4 + i] = p.b0[i];
+      for (int i = threadIdx.x; i < C2; i += Cfg::ROWS) cst[C1 * 5 + i] = p.b1[i];
+      for (int i = threadIdx.x; i < C3; i += Cfg::ROWS) cst[C1 * 5 + C2 + i] = p.b2[i];
     }
     if (D > 0) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      SA_BAR();
       constexpr int CPR = D / 8;                 // 16-byte chunks per row
-      constexpr int TOTAL = 128 * CPR;
+      constexpr int TOTAL = Cfg::ROWS * CPR;
       constexpr int UNR = 8;
-      static_assert(TOTAL % (128 * UNR) == 0, "gather unroll");
-      for (int i0 = threadIdx.x; i0 < TOTAL; i0 += 128 * UNR) {
+      static_assert(TOTAL % (Cfg::ROWS * UNR) == 0, "gather unroll");
+      for (int i0 = threadIdx.x; i0 < TOTAL; i0 += Cfg::ROWS * UNR) {
         uint4 v[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          const int ch = i0 + u * 128;
+          const int ch = i0 + u * Cfg::ROWS;
           const int r = ch / CPR, c8 = ch % CPR;
           const long long off = src_row[r];
           v[u] = off >= 0 ? reinterpret_cast<const uint4*>(p.feats + off * D)[c8] : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          const int ch = i0 + u * 128;
+          const int ch = i0 + u * Cfg::ROWS;
           const int r = ch / CPR, c8 = ch % CPR;
-          *reinterpret_cast<uint4*>(xa + xoff(r, c8 * 8)) = v[u];
+          *reinterpret_cast<uint4*>(bp + Cfg::OFF_X + (r >> 7) * Cfg::X_BYTES + xoff(r & 127, c8 * 8)) = v[u];
         }
       }
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  SA_BAR();
 
   int w_it = 0;  // consumer position in the weight ring (thread 32 only)
   uint32_t acc_phase = 0;
+  const int row = wq * 32 + lane;                                     // row inside this thread's sub-tile
+  uint8_t* xsub = bp + Cfg::OFF_X + sub * Cfg::X_BYTES;                // this sub-tile's operand buffer
+  const float* cst = reinterpret_cast<const float*>(bp + Cfg::OFF_CONST);
 
   // ---------------- layers 0 and 1: rows on M ----------------
 #pragma unroll
@@ -251,9 +262,6 @@ __global__ void __launch_bounds__(160)
     const int PANELS = layer == 0 ? Cfg::P0 : Cfg::P1;
     const int NB = layer == 0 ? Cfg::NB1 : Cfg::NB2;
     const int COUT = layer == 0 ? C1 : C2;
-    const uint32_t xin = base + Cfg::OFF_X;
-    uint8_t* xout = bp + Cfg::OFF_X;
-    const float* cst = reinterpret_cast<const float*>(bp + Cfg::OFF_CONST);
     const float* bias = cst + (layer == 0 ? C1 * 4 : C1 * 5);
     const bool has_mma = !(layer == 0 && D == 0);
     if (has_mma && threadIdx.x == 32) {
@@ -263,9 +271,12 @@ __global__ void __launch_bounds__(160)
           const int s = w_it % STAGES;
           mbar_wait(bar_full + 8 * s, (w_it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = desc_kmajor(xin + kp * SF_TILE), db = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE);
-          const int ks = 4;
-          for (int k = 0; k < ks; ++k) umma_bf16(tmem + nb * 128, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
+          const uint64_t db = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE);
+#pragma unroll
+          for (int t = 0; t < SUB; ++t) {
+            const uint64_t da = desc_kmajor(base + Cfg::OFF_X + t * Cfg::X_BYTES + kp * SF_TILE);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem + t * Cfg::CW + nb * 128, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
+          }
           umma_commit(bar_empty + 8 * s);
           ++w_it;
         }
@@ -278,9 +289,8 @@ __global__ void __launch_bounds__(160)
       acc_phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    // epilogue: thread = row; (+ xyz terms) + bias + ReLU -> bf16 -> next operand tile
-    const int row = warp * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    // epilogue: thread = row; (+ xyz terms) + bias + ReLU -> bf16 -> next operand tile (in place)
+    const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16) + sub * Cfg::CW;
 #pragma unroll 1
     for (int c = 0; c < COUT / 32; ++c) {
       uint32_t v[32];
@@ -308,18 +318,17 @@ __global__ void __launch_bounds__(160)
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<uint4*>(xout + xoff(row, c * 32 + i * 8)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        *reinterpret_cast<uint4*>(xsub + xoff(row, c * 32 + i * 8)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    SA_BAR();
   }
 
   // ---------------- layer 2: channels on M (one 128-channel block at a time), rows on N ----------------
   {
-    const uint32_t xin = base + Cfg::OFF_X;
-    const float* b2s = reinterpret_cast<const float*>(bp + Cfg::OFF_CONST) + C1 * 5 + C2;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const float* b2s = cst + C1 * 5 + C2;
+    const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16) + sub * 128;
 #pragma unroll 1
     for (int mb = 0; mb < Cfg::MB3; ++mb) {
       if (threadIdx.x == 32) {
@@ -328,8 +337,12 @@ __global__ void __launch_bounds__(160)
           const int s = w_it % STAGES;
           mbar_wait(bar_full + 8 * s, (w_it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE), db = desc_kmajor(xin + kp * SF_TILE);
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
+          const uint64_t da = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE);
+#pragma unroll
+          for (int t = 0; t < SUB; ++t) {
+            const uint64_t db = desc_kmajor(base + Cfg::OFF_X + t * Cfg::X_BYTES + kp * SF_TILE);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem + t * 128, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
+          }
           umma_commit(bar_empty + 8 * s);
           ++w_it;
         }
@@ -339,10 +352,10 @@ __global__ void __launch_bounds__(160)
       mbar_wait(bar_acc, acc_phase);
       acc_phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int ch = mb * 128 + warp * 32 + lane;
+      const int ch = mb * 128 + wq * 32 + lane;
       const float bias = b2s[ch];
 #pragma unroll 1
-      for (int g = 0; g < Cfg::G; ++g) {
+      for (int g = 0; g < Cfg::GS; ++g) {
         float m = -INFINITY;
 #pragma unroll
         for (int c = 0; c < NS / 32; ++c) {
@@ -352,17 +365,16 @@ __global__ void __launch_bounds__(160)
 #pragma unroll
           for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
         }
-        const long long grp = g0 + g;
+        const long long grp = g0 + sub * Cfg::GS + g;
         if (grp < p.groups) p.out[grp * C3 + ch] = __float2bfloat16_rn(fmaxf(m + bias, 0.f));
       }
-      // the next channel block reuses the same TMEM columns: all four warps must have drained them
+      // the next channel block reuses the same TMEM columns: every compute warp must have drained them
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      SA_BAR();
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  asm volatile("bar.sync 1, 128;" ::: "memory");
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS));
+#undef SA_BAR
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
@@ -390,9 +402,9 @@ int weight_map(CUtensorMap* map, const void* w, int rows, int cols, int ld) {
   return r == CUDA_SUCCESS ? PFPP_OK : PFPP_EINVAL;
 }
 
-template <int NS, int D, int C1, int C2, int C3, int STAGES>
+template <int NS, int D, int C1, int C2, int C3, int STAGES, int SUB>
 int launch_sa(const SaParams& p, const void* w0, const void* w1, const void* w2, cudaStream_t stream) {
-  using Cfg = SaCfg<NS, D, C1, C2, C3, STAGES>;
+  using Cfg = SaCfg<NS, D, C1, C2, C3, STAGES, SUB>;
   static_assert(D % 64 == 0 && C1 % 64 == 0 && C2 % 64 == 0 && C3 % 128 == 0, "panel-aligned channel counts");
   CUtensorMap m0, m1, m2;
   int rc = D > 0 ? weight_map(&m0, w0, C1, D, D) : weight_map(&m0, w1, C2, C1, C1);  // m0 unused when D == 0
@@ -401,10 +413,10 @@ int launch_sa(const SaParams& p, const void* w0, const void* w1, const void* w2,
   if (rc) return rc;
   rc = weight_map(&m2, w2, C3, C2, C2);
   if (rc) return rc;
-  auto kern = sa_fused_kernel<NS, D, C1, C2, C3, STAGES>;
+  auto kern = sa_fused_kernel<NS, D, C1, C2, C3, STAGES, SUB>;
   PFPP_ENSURE_SMEM(kern, Cfg::SMEM);
   const long long tiles = (p.groups + Cfg::G - 1) / Cfg::G;
-  kern<<<(unsigned)tiles, 160, Cfg::SMEM, stream>>>(m0, m1, m2, p);
+  kern<<<(unsigned)tiles, Cfg::THREADS, Cfg::SMEM, stream>>>(m0, m1, m2, p);
   PFPP_RETURN_LAST();
 }
 
@@ -419,13 +431,13 @@ extern "C" int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, 
              (long long)K * S};
   switch (level) {
     case 1:
-      return launch_sa<32, 0, 64, 64, 128, 2>(p, w0_feat, w1, w2, stream);
+      return launch_sa<32, 0, 64, 64, 128, 2, 1>(p, w0_feat, w1, w2, stream);
     case 2:
       PFPP_CHECK_ARG(feats && w0_feat);
-      return launch_sa<64, 128, 128, 128, 256, 2>(p, w0_feat, w1, w2, stream);
+      return launch_sa<64, 128, 128, 128, 256, 2, 2>(p, w0_feat, w1, w2, stream);
     case 3:
       PFPP_CHECK_ARG(feats && w0_feat);
-      return launch_sa<64, 256, 256, 256, 512, 2>(p, w0_feat, w1, w2, stream);
+      return launch_sa<64, 256, 256, 256, 512, 2, 2>(p, w0_feat, w1, w2, stream);
     default:
       return PFPP_EINVAL;
   }
