@@ -278,6 +278,185 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// Coalesced epilogue for one 32-row x 32-column accumulator chunk owned by one warp.
+// tcgen05.ld hands every thread ONE ROW (32 consecutive columns); storing that directly makes each warp
+// store touch 32 different rows (16-byte pieces, 32 partial sectors) -- measured 2-3x slower than the main
+// loop.  Instead the warp transposes the chunk through a private 4 KB shared-memory tile (16-byte chunks
+// XOR-swizzled by row, conflict-free both ways) so that in the second phase 8 consecutive lanes cover one
+// 128-byte row segment: every global load (residual) and store is a fully coalesced line segment.  Bias,
+// activation / GEGLU and the fp32 residual add happen in the second phase on 4 consecutive columns per lane.
+template <int EPI, bool OUT_BF16>
+__device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t* v, float* stage, int lane, int row0, int nb,
+                                                         int M, int N, const float* __restrict__ bias,
+                                                         const float* residual, int ldr, void* Cout, int ldc) {
+  // phase 1: thread = row `lane` of the chunk; 8 x 16-byte chunks, chunk j stored at slot j ^ (lane & 7)
+  uint4* srow = reinterpret_cast<uint4*>(stage) + lane * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) srow[j ^ (lane & 7)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  // phase 2: lane -> (row r = lane/8 + 4 i, column group c = lane % 8 -> columns nb + 4c .. 4c+3)
+  const int c = lane & 7;
+  const int n = nb + 4 * c;
+  float b4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < N) b4[j] = bias[n + j];
+  }
+  // residual rows are fetched up front (8 independent 16-byte loads in flight per lane): residual may alias
+  // Cout, so the compiler cannot hoist these loads above the stores of earlier rows by itself
+  float4 res[8];
+  const bool vec_res = residual && (n + 4 <= N) && (ldr % 4) == 0;
+  if (vec_res) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + (lane >> 3) + 4 * i;
+      res[i] = row < M ? *reinterpret_cast<const float4*>(residual + (size_t)row * ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (lane >> 3) + 4 * i;
+    const int row = row0 + r;
+    const uint4 raw = reinterpret_cast<const uint4*>(stage)[r * 8 + (c ^ (r & 7))];
+    if (row >= M || n >= N) continue;
+    float a[4] = {__uint_as_float(raw.x) + b4[0], __uint_as_float(raw.y) + b4[1], __uint_as_float(raw.z) + b4[2],
+                  __uint_as_float(raw.w) + b4[3]};
+    if (EPI == PFPP_EPI_GEGLU) {
+      // interleaved (value, gate) pairs: columns (n, n+1) -> output column n/2, (n+2, n+3) -> n/2 + 1
+      const float o0 = a[0] * gelu_erf(a[1]), o1 = a[2] * gelu_erf(a[3]);
+      const size_t off = (size_t)row * ldc + (n >> 1);
+      if (OUT_BF16) {
+        if (n + 3 < N && (ldc % 2) == 0) {
+          __nv_bfloat162 p = __floats2bfloat162_rn(o0, o1);
+          *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(Cout) + off) = p;
+        } else {
+          if (n + 1 < N) reinterpret_cast<__nv_bfloat16*>(Cout)[off] = __float2bfloat16_rn(o0);
+          if (n + 3 < N) reinterpret_cast<__nv_bfloat16*>(Cout)[off + 1] = __float2bfloat16_rn(o1);
+        }
+      } else {
+        if (n + 1 < N) reinterpret_cast<float*>(Cout)[off] = o0;
+        if (n + 3 < N) reinterpret_cast<float*>(Cout)[off + 1] = o1;
+      }
+      continue;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = tc_act<EPI>(a[j]);
+    const bool full = n + 4 <= N;
+    if (vec_res) {
+      a[0] += res[i].x, a[1] += res[i].y, a[2] += res[i].z, a[3] += res[i].w;
+    } else if (residual) {
+      const float* rp = residual + (size_t)row * ldr + n;
+      for (int j = 0; j < 4; ++j)
+        if (n + j < N) a[j] += rp[j];
+    }
+    if (OUT_BF16) {
+      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * ldc + n;
+      if (full && (ldc % 4) == 0) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]), p1 = __floats2bfloat162_rn(a[2], a[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(cp) = pk;
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (n + j < N) cp[j] = __float2bfloat16_rn(a[j]);
+      }
+    } else {
+      float* cp = reinterpret_cast<float*>(Cout) + (size_t)row * ldc + n;
+      if (full && (ldc % 4) == 0) {
+        *reinterpret_cast<float4*>(cp) = make_float4(a[0], a[1], a[2], a[3]);
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (n + j < N) cp[j] = a[j];
+      }
+    }
+  }
+  __syncwarp();  // the staging tile is rewritten by the next chunk
+}
+
+// Shared epilogue for one 32-column chunk of one accumulator row (values v[32] straight from tcgen05.ld).
+template <int EPI, bool OUT_BF16>
+__device__ __forceinline__ void epilogue_store(const uint32_t* v, int row, int nb, int M, int N, const float* __restrict__ bias,
+                                               const float* residual, int ldr, void* Cout, int ldc) {
+  if (!(row < M && nb < N)) return;
+  if (EPI == PFPP_EPI_GEGLU) {
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const int n = nb + j;
+      float val = __uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f);
+      float gate = __uint_as_float(v[j + 1]) + ((bias && n + 1 < N) ? bias[n + 1] : 0.f);
+      o[j >> 1] = val * gelu_erf(gate);
+    }
+    const size_t off = (size_t)row * ldc + (nb >> 1);
+    if (nb + 32 <= N && OUT_BF16 && (ldc % 8) == 0) {
+      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + off;
+#pragma unroll
+      for (int j = 0; j < 16; j += 8) {
+        uint4 pk;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(cp + j) = pk;
+      }
+    } else {
+      for (int j = 0; j < 16; ++j) {
+        if (nb + 2 * j + 1 < N) {
+          if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(Cout)[off + j] = __float2bfloat16_rn(o[j]);
+          else reinterpret_cast<float*>(Cout)[off + j] = o[j];
+        }
+      }
+    }
+    return;
+  }
+  float o[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int n = nb + j;
+    o[j] = tc_act<EPI>(__uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f));
+  }
+  if (residual) {
+    const float* rp = residual + (size_t)row * ldr + nb;
+    if (nb + 32 <= N && (ldr % 4) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+        o[j] += r4.x, o[j + 1] += r4.y, o[j + 2] += r4.z, o[j + 3] += r4.w;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < N) o[j] += rp[j];
+    }
+  }
+  if (OUT_BF16) {
+    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * ldc + nb;
+    if (nb + 32 <= N && (ldc % 8) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(cp + j) = pk;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < N) cp[j] = __float2bfloat16_rn(o[j]);
+    }
+  } else {
+    float* cp = reinterpret_cast<float*>(Cout) + (size_t)row * ldc + nb;
+    if (nb + 32 <= N && (ldc % 4) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < N) cp[j] = o[j];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Persistent variant for the wide denoiser projections (N >= 256): 128 x 256 output tiles, a 4-stage
 // TMA ring, the fp32 accumulator double-buffered in TMEM (2 x 256 columns) and dedicated epilogue
@@ -293,24 +472,53 @@ constexpr int T2_STAGES = 4;
 constexpr uint32_t T2_A_BYTES = TC_BM * TC_BK * 2;
 constexpr uint32_t T2_B_BYTES = T2_BN * TC_BK * 2;
 constexpr uint32_t T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
-constexpr uint32_t T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t T2_EPI_STAGE_BYTES = 8 * 4096;  // 8 epilogue warps x 4 KB transpose tile
+constexpr uint32_t T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + T2_EPI_STAGE_BYTES + 1024 + 256;
 constexpr uint32_t T2_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T2_BN >> 3) << 17) |
                               ((uint32_t)(TC_BM >> 4) << 24);
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 constexpr int T2_THREADS = 64 + 256;
 
-template <int EPI, bool OUT_BF16>
+// MC = true: CTAs run as clusters of 2 that own vertically adjacent 128-row tiles of the same 256-column block.
+// Each CTA loads its own A tile and one HALF of the shared W tile, multicast into both CTAs' shared memory
+// (cp.async.bulk.tensor ... .multicast::cluster), so the W operand crosses the L2->SM fabric once per pair:
+// operand bytes per tile drop from 393 KB to 262 KB.  Stage-release (tcgen05.commit) is multicast to both
+// CTAs' empty barriers, since a stage is rewritten by both producers.
+template <int EPI, bool OUT_BF16, bool MC>
 __global__ void __launch_bounds__(T2_THREADS)
     gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const float* __restrict__ bias, const float* residual, int ldr, void* Cout, int ldc, int M,
-                         int N, int K) {
+                         int N, int K, int m_store) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + T2_STAGES * T2_STAGE_BYTES;
+  const uint32_t epi_stage = smem_base + T2_STAGES * T2_STAGE_BYTES;
+  const uint32_t bar_base = epi_stage + T2_EPI_STAGE_BYTES;
   const uint32_t bar_full = bar_base, bar_empty = bar_base + 8 * T2_STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * T2_STAGES;  // [2]
   const uint32_t bar_tempty = bar_tfull + 16;            // [2]
@@ -318,13 +526,19 @@ __global__ void __launch_bounds__(T2_THREADS)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + T2_BN - 1) / T2_BN, tiles_m = (M + TC_BM - 1) / TC_BM;
-  const int num_tiles = tiles_n * tiles_m;
   const int num_kb = (K + TC_BK - 1) / TC_BK;
+  // work items: single tiles, or (MC) vertical pairs of tiles handled by the 2 CTAs of a cluster
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  const int worker = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_items = (MC ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
+  auto item_m0 = [&](int t) { return ((MC ? 2 * (t / tiles_n) + (int)crank : t / tiles_n)) * TC_BM; };
+  auto item_n0 = [&](int t) { return (t % tiles_n) * T2_BN; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < T2_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, MC ? 2 : 1);  // MC: released by the MMA issuers of both CTAs
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
@@ -338,28 +552,35 @@ __global__ void __launch_bounds__(T2_THREADS)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * T2_BN;
+      for (int t = worker; t < num_items; t += n_workers) {
+        const int m0 = item_m0(t), n0 = item_n0(t);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % T2_STAGES, round = it / T2_STAGES;
           mbar_wait(bar_empty + 8 * s, (round & 1) ^ 1);
           mbar_expect_tx(bar_full + 8 * s, T2_STAGE_BYTES);
           const uint32_t sa = smem_base + s * T2_STAGE_BYTES;
           tma_load_2d(sa, &map_a, bar_full + 8 * s, kb * TC_BK, m0);
-          tma_load_2d(sa + T2_A_BYTES, &map_b, bar_full + 8 * s, kb * TC_BK, n0);
+          if (MC) {
+            // my half of the W tile (128 of the 256 rows) -> both CTAs, signalling each CTA's own full barrier
+            tma_load_2d_mc(sa + T2_A_BYTES + crank * (T2_B_BYTES / 2), &map_b, bar_full + 8 * s, kb * TC_BK,
+                           n0 + (int)crank * (T2_BN / 2), (uint16_t)0x3);
+          } else {
+            tma_load_2d(sa + T2_A_BYTES, &map_b, bar_full + 8 * s, kb * TC_BK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      for (int t = worker; t < num_items; t += n_workers, ++lt) {
         const uint32_t buf = lt & 1, use = lt >> 1;
         mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -372,7 +593,8 @@ __global__ void __launch_bounds__(T2_THREADS)
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + T2_A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, T2_IDESC, (kb | k) != 0);
-          umma_commit(bar_empty + 8 * s);
+          if (MC) umma_commit_mc(bar_empty + 8 * s, (uint16_t)0x3);
+          else umma_commit(bar_empty + 8 * s);
         }
         umma_commit(bar_tfull + 8 * buf);
       }
@@ -381,97 +603,20 @@ __global__ void __launch_bounds__(T2_THREADS)
     const int q = warp & 3;                 // TMEM lane quarter
     const int chalf = (warp - 2) >> 2;      // which 128-column half of the tile this warp drains
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+    for (int t = worker; t < num_items; t += n_workers, ++lt) {
       const uint32_t buf = lt & 1, use = lt >> 1;
-      const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * T2_BN;
+      const int m0 = item_m0(t), n0 = item_n0(t);
       mbar_wait(bar_tfull + 8 * buf, use & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + buf * T2_BN + ((uint32_t)(q * 32) << 16);
+      float* stage = reinterpret_cast<float*>(smem_raw + (epi_stage - smem_u32(smem_raw)) + (warp - 2) * 4096);
 #pragma unroll 1
       for (int c = chalf * (T2_BN / 64); c < (chalf + 1) * (T2_BN / 64); ++c) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int nb = n0 + c * 32;
-        if (row < M && nb < N) {
-          if (EPI == PFPP_EPI_GEGLU) {
-            float o[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int n = nb + j;
-              float val = __uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f);
-              float gate = __uint_as_float(v[j + 1]) + ((bias && n + 1 < N) ? bias[n + 1] : 0.f);
-              o[j >> 1] = val * gelu_erf(gate);
-            }
-            const size_t off = (size_t)row * ldc + (nb >> 1);
-            if (nb + 32 <= N && OUT_BF16 && (ldc % 8) == 0) {
-              __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + off;
-#pragma unroll
-              for (int j = 0; j < 16; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                *reinterpret_cast<uint4*>(cp + j) = pk;
-              }
-            } else {
-              for (int j = 0; j < 16; ++j) {
-                if (nb + 2 * j + 1 < N) {
-                  if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(Cout)[off + j] = __float2bfloat16_rn(o[j]);
-                  else reinterpret_cast<float*>(Cout)[off + j] = o[j];
-                }
-              }
-            }
-          } else {
-            float o[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = nb + j;
-              o[j] = tc_act<EPI>(__uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f));
-            }
-            if (residual) {
-              const float* rp = residual + (size_t)row * ldr + nb;
-              if (nb + 32 <= N && (ldr % 4) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-                  o[j] += r4.x, o[j + 1] += r4.y, o[j + 2] += r4.z, o[j + 3] += r4.w;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (nb + j < N) o[j] += rp[j];
-              }
-            }
-            if (OUT_BF16) {
-              __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * ldc + nb;
-              if (nb + 32 <= N && (ldc % 8) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 pk;
-                  __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-                  __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-                  pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                  pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                  *reinterpret_cast<uint4*>(cp + j) = pk;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (nb + j < N) cp[j] = __float2bfloat16_rn(o[j]);
-              }
-            } else {
-              float* cp = reinterpret_cast<float*>(Cout) + (size_t)row * ldc + nb;
-              if (nb + 32 <= N && (ldc % 4) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (nb + j < N) cp[j] = o[j];
-              }
-            }
-          }
-        }
+        epilogue_chunk_coalesced<EPI, OUT_BF16>(v, stage, lane, m0 + q * 32, n0 + c * 32, m_store, N, bias, residual, ldr,
+                                                Cout, ldc);
       }
       // this warp is done with the accumulator buffer: hand it back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -481,8 +626,176 @@ __global__ void __launch_bounds__(T2_THREADS)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (MC) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / signal its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile with
+// ONE MMA stream issued by the leader CTA.  Each CTA stages only its 128 rows of A and its 128-row half of
+// the W tile (32 KB per k-block instead of 48 KB), the tensor cores exchange the halves, and each CTA ends
+// up with its own 128 x 256 accumulator in its own TMEM.  This halves the shared-memory traffic per FLOP --
+// at 128 x 256 per single CTA the main loop is bound by shared-memory bandwidth (TMA fill + operand reads
+// ~190 B/clk/SM against 128 B/clk), not by L2 or the tensor pipe.  6-stage ring (192 KB), accumulators
+// double-buffered in TMEM, 8 epilogue warps per CTA.
+//   full[s]   : leader CTA only; both CTAs' TMA loads complete_tx on it (cta_group::2 loads)
+//   empty[s]  : per CTA; released by the leader's tcgen05.commit multicast to both CTAs
+//   tfull[b]  : per CTA; leader's commit multicast;   tempty[b] : leader only, 16 arrivals (8 warps x 2 CTAs)
+// ------------------------------------------------------------------------------------------------
+constexpr int T3_STAGES = 6;
+constexpr uint32_t T3_HALF_BYTES = 128 * TC_BK * 2;            // one [128 x 64] operand half = 16 KB
+constexpr uint32_t T3_STAGE_BYTES = 2 * T3_HALF_BYTES;          // A half + W half per CTA
+constexpr uint32_t T3_SMEM_BYTES = T3_STAGES * T3_STAGE_BYTES + T2_EPI_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t T3_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;                 // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(local_bar),
+      "r"(cta_rank)
+      : "memory");
+}
+
+template <int EPI, bool OUT_BF16>
+__global__ void __launch_bounds__(T2_THREADS)
+    gemm_bf16_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const float* __restrict__ bias, const float* residual, int ldr, void* Cout, int ldc, int M,
+                         int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_stage = smem_base + T3_STAGES * T3_STAGE_BYTES;
+  const uint32_t bar_base = epi_stage + T2_EPI_STAGE_BYTES;
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 8 * T3_STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * T3_STAGES;  // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;            // [2]
+  const uint32_t tmem_slot = bar_tempty + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int tiles_n = (N + 255) / 256, tiles_mp = (M + 255) / 256;
+  const int num_items = tiles_mp * tiles_n;
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int worker = (int)(blockIdx.x >> 1), n_workers = (int)(gridDim.x >> 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T3_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 16);  // 8 epilogue warps of each of the two CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = worker; t < num_items; t += n_workers) {
+        const int m0 = (t / tiles_n) * 256 + (int)crank * 128, n0 = (t % tiles_n) * 256 + (int)crank * 128;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % T3_STAGES, round = it / T3_STAGES;
+          mbar_wait(bar_empty + 8 * s, (round & 1) ^ 1);
+          const uint32_t lead_full = (bar_full + 8 * s) & PEER_BIT_MASK;
+          if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * T3_STAGE_BYTES);  // both CTAs' halves
+          const uint32_t sa = smem_base + s * T3_STAGE_BYTES;
+          tma_load_2d_2sm(sa, &map_a, lead_full, kb * TC_BK, m0);
+          tma_load_2d_2sm(sa + T3_HALF_BYTES, &map_b, lead_full, kb * TC_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      uint32_t it = 0, lt = 0;
+      for (int t = worker; t < num_items; t += n_workers, ++lt) {
+        const uint32_t buf = lt & 1, use = lt >> 1;
+        mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);  // both CTAs' epilogues have drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + buf * 256;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % T3_STAGES, round = it / T3_STAGES;
+          mbar_wait(bar_full + 8 * s, round & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + s * T3_STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + T3_HALF_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) umma_bf16_2sm(acc, da + 2 * k, db + 2 * k, T3_IDESC, (kb | k) != 0);
+          umma_commit_2sm_mc(bar_empty + 8 * s, (uint16_t)0x3);
+        }
+        umma_commit_2sm_mc(bar_tfull + 8 * buf, (uint16_t)0x3);
+      }
+    }
+  } else {
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int chalf = (warp - 2) >> 2;      // which 128-column half of the tile this warp drains
+    uint32_t lt = 0;
+    for (int t = worker; t < num_items; t += n_workers, ++lt) {
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      const int m0 = (t / tiles_n) * 256 + (int)crank * 128, n0 = (t % tiles_n) * 256;
+      mbar_wait(bar_tfull + 8 * buf, use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+      float* stage = reinterpret_cast<float*>(smem_raw + (epi_stage - smem_u32(smem_raw)) + (warp - 2) * 4096);
+#pragma unroll 1
+      for (int c = chalf * 4; c < (chalf + 1) * 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        epilogue_chunk_coalesced<EPI, OUT_BF16>(v, stage, lane, m0 + q * 32, n0 + c * 32, M, N, bias, residual, ldr, Cout,
+                                                ldc);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(bar_tempty + 8 * buf);
+        else mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -523,19 +836,76 @@ int sm_count() {
   return n;
 }
 
+template <int EPI, bool OUT_BF16, bool MC>
+int launch_tc2_impl(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* residual, int ldr,
+                    void* C, int ldc, int M, int N, int K, cudaStream_t stream) {
+  auto kern = gemm_bf16_tc2_kernel<EPI, OUT_BF16, MC>;
+  PFPP_ENSURE_SMEM(kern, T2_SMEM_BYTES);
+  const int tiles_n = pfpp_cdiv(N, T2_BN), tiles_m = pfpp_cdiv(M, TC_BM);
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(T2_THREADS);
+  cfg.dynamicSmemBytes = T2_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (MC) {
+    const int items = ((tiles_m + 1) / 2) * tiles_n;
+    int grid = 2 * items < sm_count() ? 2 * items : (sm_count() & ~1);
+    cfg.gridDim = dim3(grid);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    const int tiles = tiles_n * tiles_m;
+    cfg.gridDim = dim3(tiles < sm_count() ? tiles : sm_count());
+  }
+  static const int nostore = getenv("PFPP_GEMM_DEBUG_NOSTORE") ? 1 : 0;  // ablation knob (results are not written)
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, bias, residual, ldr, C, ldc, M, N, K, nostore ? 0 : M);
+  if (e != cudaSuccess) return (int)e;
+  PFPP_RETURN_LAST();
+}
+
 template <int EPI>
 int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* residual, int ldr, void* C,
-               int ldc, int c_bf16, int M, int N, int K, cudaStream_t stream) {
-  const int tiles = pfpp_cdiv(N, T2_BN) * pfpp_cdiv(M, TC_BM);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  if (c_bf16) {
-    PFPP_ENSURE_SMEM((gemm_bf16_tc2_kernel<EPI, true>), T2_SMEM_BYTES);
-    gemm_bf16_tc2_kernel<EPI, true><<<grid, T2_THREADS, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
-  } else {
-    PFPP_ENSURE_SMEM((gemm_bf16_tc2_kernel<EPI, false>), T2_SMEM_BYTES);
-    gemm_bf16_tc2_kernel<EPI, false><<<grid, T2_THREADS, T2_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
+               int ldc, int c_bf16, int M, int N, int K, bool mc, cudaStream_t stream) {
+  if (mc) {
+    return c_bf16 ? launch_tc2_impl<EPI, true, true>(ma, mb, bias, residual, ldr, C, ldc, M, N, K, stream)
+                  : launch_tc2_impl<EPI, false, true>(ma, mb, bias, residual, ldr, C, ldc, M, N, K, stream);
   }
+  return c_bf16 ? launch_tc2_impl<EPI, true, false>(ma, mb, bias, residual, ldr, C, ldc, M, N, K, stream)
+                : launch_tc2_impl<EPI, false, false>(ma, mb, bias, residual, ldr, C, ldc, M, N, K, stream);
+}
+
+template <int EPI, bool OUT_BF16>
+int launch_tc3_impl(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* residual, int ldr,
+                    void* C, int ldc, int M, int N, int K, cudaStream_t stream) {
+  auto kern = gemm_bf16_tc3_kernel<EPI, OUT_BF16>;
+  PFPP_ENSURE_SMEM(kern, T3_SMEM_BYTES);
+  const int items = pfpp_cdiv(M, 256) * pfpp_cdiv(N, 256);
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(T2_THREADS);
+  cfg.dynamicSmemBytes = T3_SMEM_BYTES;
+  cfg.stream = stream;
+  cfg.gridDim = dim3(2 * items < sm_count() ? 2 * items : (sm_count() & ~1));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, bias, residual, ldr, C, ldc, M, N, K);
+  if (e != cudaSuccess) return (int)e;
   PFPP_RETURN_LAST();
+}
+
+template <int EPI>
+int launch_tc3(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* residual, int ldr, void* C,
+               int ldc, int c_bf16, int M, int N, int K, cudaStream_t stream) {
+  return c_bf16 ? launch_tc3_impl<EPI, true>(ma, mb, bias, residual, ldr, C, ldc, M, N, K, stream)
+                : launch_tc3_impl<EPI, false>(ma, mb, bias, residual, ldr, C, ldc, M, N, K, stream);
 }
 
 template <int EPI>
@@ -566,27 +936,44 @@ extern "C" int pfpp_gemm_bf16(const void* A, int lda, const void* W, int ldw, co
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, lda, TC_BM);
   if (rc) return rc;
-  // persistent 128x256 kernel for the wide projections; the GEGLU epilogue (128 erf per row per tile) is
-  // better spread over the 2 CTAs/SM of the 128x128 kernel (measured: 183 vs 254 us at M=16000, N=4096)
   static const int v2_mode = []() {
-    const char* e = getenv("PFPP_GEMM_V2");  // 0 = never, 1 = default policy, 2 = always (tuning knob)
-    return e ? atoi(e) : 1;
+    // 0 = 128x128 kernel only, 1 = persistent 128x256, 2 = + cluster multicast of W, 3 = CTA-pair (cta_group::2)
+    const char* e = getenv("PFPP_GEMM_V2");
+    return e ? atoi(e) : 3;
   }();
-  const bool wide = N >= T2_BN && M >= 2 * TC_BM && v2_mode != 0 && (epilogue != PFPP_EPI_GEGLU || v2_mode == 2);
-  rc = make_map(&mb, W, N, K, ldw, wide ? T2_BN : TC_BN);
+  const bool wide = N >= T2_BN && M >= 2 * TC_BM && v2_mode != 0;  // persistent 128x256 kernel for the wide projections
+  const bool mc = wide && v2_mode == 2 && (N % T2_BN) == 0;
+  const bool pair = wide && v2_mode >= 3;  // cta_group::2 kernel
+  rc = make_map(&mb, W, N, K, ldw, wide ? ((mc || pair) ? T2_BN / 2 : T2_BN) : TC_BN);
   if (rc) return rc;
+  if (pair) {
+    switch (epilogue) {
+      case PFPP_EPI_NONE:
+        return launch_tc3<PFPP_EPI_NONE>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      case PFPP_EPI_RELU:
+        return launch_tc3<PFPP_EPI_RELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      case PFPP_EPI_GELU:
+        return launch_tc3<PFPP_EPI_GELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      case PFPP_EPI_SILU:
+        return launch_tc3<PFPP_EPI_SILU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      case PFPP_EPI_GEGLU:
+        return launch_tc3<PFPP_EPI_GEGLU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+      default:
+        return PFPP_EINVAL;
+    }
+  }
   if (wide) {
     switch (epilogue) {
       case PFPP_EPI_NONE:
-        return launch_tc2<PFPP_EPI_NONE>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+        return launch_tc2<PFPP_EPI_NONE>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
       case PFPP_EPI_RELU:
-        return launch_tc2<PFPP_EPI_RELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+        return launch_tc2<PFPP_EPI_RELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
       case PFPP_EPI_GELU:
-        return launch_tc2<PFPP_EPI_GELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+        return launch_tc2<PFPP_EPI_GELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
       case PFPP_EPI_SILU:
-        return launch_tc2<PFPP_EPI_SILU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+        return launch_tc2<PFPP_EPI_SILU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
       case PFPP_EPI_GEGLU:
-        return launch_tc2<PFPP_EPI_GEGLU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
+        return launch_tc2<PFPP_EPI_GEGLU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
       default:
         return PFPP_EINVAL;
     }

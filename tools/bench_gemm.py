@@ -29,13 +29,14 @@ def main():
         for _ in range(3):
             run()
         ts = []
-        for _ in range(20):
+        for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            run()
+            for _ in range(10):
+                run()
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e3)
+            ts.append(e0.elapsed_time(e1) * 1e3 / 10)
         ts.sort()
         t = ts[len(ts) // 2]
         print(f"{name:10s} M={M} N={N} K={K}: {t:7.1f} us  {2.0 * M * N * K / t / 1e6:7.1f} TFLOP/s")
