@@ -43,6 +43,15 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// tanh-form GELU on the MUFU pipe, used ONLY where the result is immediately rounded to bf16 (GEGLU hidden of
+// the tensor-core path): |gelu_tanh - gelu_erf| <= 5e-4 absolute, below half a bf16 ulp of the product it
+// feeds; the fp32 (parity) kernels keep the exact erf form.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  float t;
+  const float u = 0.7978845608028654f * fmaf(0.044715f * x, x * x, x);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

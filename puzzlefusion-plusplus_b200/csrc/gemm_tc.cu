@@ -374,6 +374,64 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t* v, floa
   __syncwarp();  // the staging tile is rewritten by the next chunk
 }
 
+// bf16 outputs: the warp converts its 32 rows x 64 output columns to bf16, lays them out as a 128B-swizzled
+// [32 x 128 B] box in its private shared-memory tile and hands the box to the TMA engine
+// (cp.async.bulk.tensor store): the SM issues no global stores at all and the write is full-line.
+// NCH = accumulator chunks (32 columns each) feeding one 64-column output slab: 2, or 4 for GEGLU.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_slab_tma(uint32_t taddr, int acc_col0, uint8_t* stage, uint32_t stage_addr, int lane,
+                                                  int row0, int out_col0, int n_acc0, int N, const float* __restrict__ bias,
+                                                  const CUtensorMap* map_c) {
+  constexpr int NCH = EPI == PFPP_EPI_GEGLU ? 4 : 2;
+  uint32_t pk[32];  // 64 bf16 of this thread's row
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint32_t v[32];
+    tmem_ld32(taddr + (uint32_t)(acc_col0 + ch * 32), v);
+    const int nb = n_acc0 + ch * 32;
+    float bl = 0.f;
+    if (bias && nb + lane < N) bl = bias[nb + lane];  // one coalesced load; broadcast by shuffle below
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (EPI == PFPP_EPI_GEGLU) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float v0 = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
+        const float g0 = __uint_as_float(v[j + 1]) + __shfl_sync(0xffffffffu, bl, j + 1);
+        const float v1 = __uint_as_float(v[j + 2]) + __shfl_sync(0xffffffffu, bl, j + 2);
+        const float g1 = __uint_as_float(v[j + 3]) + __shfl_sync(0xffffffffu, bl, j + 3);
+        __nv_bfloat162 p = __floats2bfloat162_rn(v0 * gelu_tanh_fast(g0), v1 * gelu_tanh_fast(g1));
+        pk[ch * 8 + (j >> 2)] = *reinterpret_cast<uint32_t*>(&p);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float a = tc_act<EPI>(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j));
+        const float b = tc_act<EPI>(__uint_as_float(v[j + 1]) + __shfl_sync(0xffffffffu, bl, j + 1));
+        __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+        pk[ch * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&p);
+      }
+    }
+  }
+  // the previous box of this warp must have been read out of shared memory before it is overwritten
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+  uint4* srow = reinterpret_cast<uint4*>(stage) + lane * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) srow[j ^ (lane & 7)] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(map_c, stage_addr, out_col0, row0);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
 // Shared epilogue for one 32-column chunk of one accumulator row (values v[32] straight from tcgen05.ld).
 template <int EPI, bool OUT_BF16>
 __device__ __forceinline__ void epilogue_store(const uint32_t* v, int row, int nb, int M, int N, const float* __restrict__ bias,
@@ -687,8 +745,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 template <int EPI, bool OUT_BF16>
 __global__ void __launch_bounds__(T2_THREADS)
     gemm_bf16_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         const float* __restrict__ bias, const float* residual, int ldr, void* Cout, int ldc, int M,
-                         int N, int K) {
+                         const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, const float* residual,
+                         int ldr, void* Cout, int ldc, int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_stage = smem_base + T3_STAGES * T3_STAGE_BYTES;
@@ -775,6 +833,26 @@ __global__ void __launch_bounds__(T2_THREADS)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
       float* stage = reinterpret_cast<float*>(smem_raw + (epi_stage - smem_u32(smem_raw)) + (warp - 2) * 4096);
+      if (OUT_BF16 && residual == nullptr) {
+        // bf16 outputs (QKV, GEGLU hidden): shared-memory box + TMA store, 64 output columns per box
+        const uint32_t stage_addr = epi_stage + (warp - 2) * 4096;
+        if (EPI == PFPP_EPI_GEGLU) {
+          epilogue_slab_tma<EPI>(taddr, chalf * 128, reinterpret_cast<uint8_t*>(stage), stage_addr, lane, m0 + q * 32,
+                                 (n0 >> 1) + chalf * 64, n0 + chalf * 128, N, bias, &map_c);
+        } else {
+#pragma unroll 1
+          for (int sl = 0; sl < 2; ++sl)
+            epilogue_slab_tma<EPI>(taddr, chalf * 128 + sl * 64, reinterpret_cast<uint8_t*>(stage), stage_addr, lane,
+                                   m0 + q * 32, n0 + chalf * 128 + sl * 64, n0 + chalf * 128 + sl * 64, N, bias, &map_c);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(bar_tempty + 8 * buf);
+          else mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = chalf * 4; c < (chalf + 1) * 4; ++c) {
         uint32_t v[32];
@@ -791,6 +869,7 @@ __global__ void __launch_bounds__(T2_THREADS)
       }
     }
   }
+  if (OUT_BF16 && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // TMA stores done
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync_all();
@@ -882,6 +961,20 @@ template <int EPI, bool OUT_BF16>
 int launch_tc3_impl(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* residual, int ldr,
                     void* C, int ldc, int M, int N, int K, cudaStream_t stream) {
   auto kern = gemm_bf16_tc3_kernel<EPI, OUT_BF16>;
+  CUtensorMap mc = ma;  // placeholder when the TMA-store path is not taken
+  if (OUT_BF16 && residual == nullptr) {
+    // output boxes of [32 rows x 64 bf16], 128B-swizzled like the staging tile
+    auto fn = get_encode_fn();
+    if (!fn) return PFPP_EUNSUPPORTED;
+    const int n_out = EPI == PFPP_EPI_GEGLU ? N / 2 : N;
+    cuuint64_t dims[2] = {(cuuint64_t)n_out, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ldc * 2};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    if (fn(&mc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return PFPP_EINVAL;
+  }
   PFPP_ENSURE_SMEM(kern, T3_SMEM_BYTES);
   const int items = pfpp_cdiv(M, 256) * pfpp_cdiv(N, 256);
   cudaLaunchConfig_t cfg{};
@@ -896,7 +989,7 @@ int launch_tc3_impl(const CUtensorMap& ma, const CUtensorMap& mb, const float* b
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, bias, residual, ldr, C, ldc, M, N, K);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, bias, residual, ldr, C, ldc, M, N, K);
   if (e != cudaSuccess) return (int)e;
   PFPP_RETURN_LAST();
 }
@@ -943,7 +1036,7 @@ extern "C" int pfpp_gemm_bf16(const void* A, int lda, const void* W, int ldw, co
   }();
   const bool wide = N >= T2_BN && M >= 2 * TC_BM && v2_mode != 0;  // persistent 128x256 kernel for the wide projections
   const bool mc = wide && v2_mode == 2 && (N % T2_BN) == 0;
-  const bool pair = wide && v2_mode >= 3;  // cta_group::2 kernel
+  const bool pair = wide && v2_mode >= 3 && (!c_bf16 || (ldc % 8) == 0);  // cta_group::2 kernel (bf16 C through TMA stores)
   rc = make_map(&mb, W, N, K, ldw, wide ? ((mc || pair) ? T2_BN / 2 : T2_BN) : TC_BN);
   if (rc) return rc;
   if (pair) {
