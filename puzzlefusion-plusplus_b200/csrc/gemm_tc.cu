@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128)
           const int n = nb + j;
           float val = __uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f);
           float gate = __uint_as_float(v[j + 1]) + ((bias && n + 1 < N) ? bias[n + 1] : 0.f);
-          o[j >> 1] = val * gelu_erf(gate);
+          o[j >> 1] = val * (OUT_BF16 ? gelu_tanh_fast(gate) : gelu_erf(gate));
         }
         const size_t off = (size_t)row * ldc + (nb >> 1);
         if (nb + 32 <= N && OUT_BF16 && (ldc % 8) == 0) {
@@ -324,7 +324,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t* v, floa
                   __uint_as_float(raw.w) + b4[3]};
     if (EPI == PFPP_EPI_GEGLU) {
       // interleaved (value, gate) pairs: columns (n, n+1) -> output column n/2, (n+2, n+3) -> n/2 + 1
-      const float o0 = a[0] * gelu_erf(a[1]), o1 = a[2] * gelu_erf(a[3]);
+      const float o0 = a[0] * (OUT_BF16 ? gelu_tanh_fast(a[1]) : gelu_erf(a[1]));
+      const float o1 = a[2] * (OUT_BF16 ? gelu_tanh_fast(a[3]) : gelu_erf(a[3]));
       const size_t off = (size_t)row * ldc + (n >> 1);
       if (OUT_BF16) {
         if (n + 3 < N && (ldc % 2) == 0) {
@@ -444,7 +445,7 @@ __device__ __forceinline__ void epilogue_store(const uint32_t* v, int row, int n
       const int n = nb + j;
       float val = __uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f);
       float gate = __uint_as_float(v[j + 1]) + ((bias && n + 1 < N) ? bias[n + 1] : 0.f);
-      o[j >> 1] = val * gelu_erf(gate);
+      o[j >> 1] = val * (OUT_BF16 ? gelu_tanh_fast(gate) : gelu_erf(gate));
     }
     const size_t off = (size_t)row * ldc + (nb >> 1);
     if (nb + 32 <= N && OUT_BF16 && (ldc % 8) == 0) {
