@@ -140,14 +140,22 @@ int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_off, int v_o
                           const int* seg_len, int n_segments, int max_len, int heads, int head_dim, int io_bf16,
                           void* out, int ldo, cudaStream_t stream);
 
-/* The denoiser's global attention (attention.py:84: diffusers Attention with the key mask) on the
- * tensor cores: bf16 qkv [M, 3C] (q | k | v, head h at columns h*64), segments of <= 512 tokens,
- * head_dim 64; S = QK^T and O = PV run as tcgen05.mma with fp32 accumulators in TMEM, operands by TMA.
- * block > 0 additionally restricts attention to aligned blocks of `block` tokens inside a segment:
- * the block-diagonal local attention (attention.py:79 with self_mask, denoiser_transformer.py:158-166),
- * run on segments of 5 fragments (125 tokens).  out is bf16 [M, C]. */
+/* The denoiser's attention (attention.py:75-92 through diffusers Attention) on the tensor cores: bf16 qkv
+ * [M, 3C] (q | k | v, head h at columns h*64), head_dim 64, one CTA per (segment, head); S = QK^T and
+ * O = PV run as tcgen05.mma with fp32 accumulators in TMEM, operands by TMA, online softmax.
+ * block == 0: global attention (attention.py:84 with the key mask): every token of a segment (one object's
+ *   valid fragments, <= 512 tokens) attends to the whole segment.
+ * block  > 0: the block-diagonal local attention (attention.py:79 with self_mask,
+ *   denoiser_transformer.py:158-166): tokens attend inside aligned blocks of `block` tokens; a segment holds
+ *   up to 4 tiles of floor(128/block) blocks (block 25: 125-token tiles, segments <= 500 tokens) and
+ *   seg_start/seg_len must be multiples of the tile length (the last segment may be short).
+ * out is bf16 [M, C]. */
 int pfpp_attention_tc(const void* qkv, long long M, int ld, int C, const int* seg_start, const int* seg_len,
                       int n_segments, int max_len, int heads, int block, void* out, int ldo, cudaStream_t stream);
+/* debug variant of pfpp_attention_tc: per-CTA clock stamps of the pipeline phases into trace[n_ctas][48] */
+int pfpp_attention_tc_trace(const void* qkv, long long M, int ld, int C, const int* seg_start, const int* seg_len,
+                            int n_segments, int max_len, int heads, int block, void* out, int ldo, long long* trace,
+                            cudaStream_t stream);
 
 /* mean over L (denoiser_transformer.py:141-142). */
 int pfpp_mean_pool(const float* h, int F, int L, int C, int out_bf16, void* out, cudaStream_t stream);

@@ -132,6 +132,91 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Small-M variant: 64x64x16 CTA tile, 256 threads, 4x4 register micro-tile.  Used when the 128x128 grid would
+// leave most of the 148 SMs idle (the denoiser's output heads: M = number of fragments).  Every output element
+// is still one sequential fmaf chain over k = 0..K-1, so both variants produce bit-identical results.
+#define SBM 64
+#define SBN 64
+template <int EPI>
+__global__ void __launch_bounds__(256)
+    gemm_f32_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                          const float* __restrict__ bias, const float* residual, int ldr, float* C, int ldc, int M,
+                          int N, int K) {
+  __shared__ __align__(16) float As[2][GBK][SBM + GPAD];
+  __shared__ __align__(16) float Ws[2][GBK][SBN + GPAD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  const int lrow = tid >> 2;     // 0..63
+  const int lk = (tid & 3) * 4;  // 0,4,8,12
+  float4 ra, rw;
+  auto load_tiles = [&](int k0) {
+    const int gm = m0 + lrow, gn = n0 + lrow, gk = k0 + lk;
+    ra = (gm < M && gk < K) ? *reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rw = (gn < N && gk < K) ? *reinterpret_cast<const float4*>(W + (size_t)gn * ldw + gk) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto store_tiles = [&](int buf) {
+    As[buf][lk + 0][lrow] = ra.x, As[buf][lk + 1][lrow] = ra.y, As[buf][lk + 2][lrow] = ra.z, As[buf][lk + 3][lrow] = ra.w;
+    Ws[buf][lk + 0][lrow] = rw.x, Ws[buf][lk + 1][lrow] = rw.y, Ws[buf][lk + 2][lrow] = rw.z, Ws[buf][lk + 3][lrow] = rw.w;
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int nk = (K + GBK - 1) / GBK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * GBK);
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+    const int gn = n0 + tx * 4;
+    if (EPI == PFPP_EPI_GEGLU) {
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const int n = gn + j;
+        if (n + 1 < N) {
+          const float v = acc[i][j] + (bias ? bias[n] : 0.f);
+          const float g = acc[i][j + 1] + (bias ? bias[n + 1] : 0.f);
+          C[(size_t)gm * ldc + (n >> 1)] = v * gelu_erf(g);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = gn + j;
+        if (n < N) {
+          float v = acc[i][j] + (bias ? bias[n] : 0.f);
+          v = apply_act<EPI>(v);
+          if (residual) v += residual[(size_t)gm * ldr + n];
+          C[(size_t)gm * ldc + n] = v;
+        }
+      }
+    }
+  }
+}
+
 extern "C" int pfpp_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
                              const float* residual, int ldr, float* C, int ldc, int M, int N, int K, int epilogue,
                              cudaStream_t stream) {
@@ -140,9 +225,14 @@ extern "C" int pfpp_gemm_f32(const float* A, int lda, const float* W, int ldw, c
   PFPP_CHECK_ARG((((uintptr_t)A) & 15) == 0 && (((uintptr_t)W) & 15) == 0);
   if (M == 0) return PFPP_OK;
   dim3 grid(pfpp_cdiv(N, GBN), pfpp_cdiv(M, GBM));
+  dim3 sgrid(pfpp_cdiv(N, SBN), pfpp_cdiv(M, SBM));
+  const bool small = grid.x * grid.y < 148;  // the big tiles would not even give every SM one CTA
 #define PFPP_GEMM_CASE(E)                                                                                      \
   case E:                                                                                                      \
-    gemm_f32_kernel<E><<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K); \
+    if (small)                                                                                                 \
+      gemm_f32_small_kernel<E><<<sgrid, 256, 0, stream>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K); \
+    else                                                                                                       \
+      gemm_f32_kernel<E><<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K);      \
     break;
   switch (epilogue) {
     PFPP_GEMM_CASE(PFPP_EPI_NONE)

@@ -61,6 +61,7 @@ class Engine:
         self.C = self.den.C
         self.tc_attention = True  # tcgen05 global attention in bf16 mode (segments <= 512 tokens)
         self.fused_sa = True     # fused gather + 3-layer MLP + max tcgen05 kernel in bf16 mode
+        self.local_tiles = 4     # 125-token tiles (5 fragments) per local-attention CTA, two per softmax group
         self._ws = {}
 
     # ------------------------------------------------------------------ helpers
@@ -86,13 +87,14 @@ class Engine:
                  M, lin.n, lin.k32, epi)
 
     def _local_tc_segments(self, F):
-        """segments of 5 fragments for the block-diagonal tensor-core attention (cached per F)."""
-        key = ("loc_tc", F)
+        """segments of `local_tiles` tiles x 5 fragments for the block-diagonal tensor-core attention (cached per F)."""
+        key = ("loc_tc", F, self.local_tiles)
         if key not in self._ws:
             L = self.L
-            n = (F + 4) // 5
-            start = torch.arange(n, dtype=torch.int32, device=self.device) * (5 * L)
-            length = torch.clamp(F * L - start, max=5 * L).to(torch.int32)
+            per = 5 * self.local_tiles  # fragments per segment
+            n = (F + per - 1) // per
+            start = torch.arange(n, dtype=torch.int32, device=self.device) * (per * L)
+            length = torch.clamp(F * L - start, max=per * L).to(torch.int32)
             self._ws[key] = (start, length)
         return self._ws[key]
 
@@ -222,7 +224,7 @@ class Engine:
                     # block-diagonal local attention: 5 fragments (125 tokens) per 128-row tensor-core tile
                     ts, tl = self._local_tc_segments(F)
                     call("pfpp_attention_tc", qkv.data_ptr(), M, 3 * C, C, ts.data_ptr(), tl.data_ptr(), ts.numel(),
-                         5 * L, H, L, ao.data_ptr(), C)
+                         5 * L * self.local_tiles, H, L, ao.data_ptr(), C)
                 else:
                     call("pfpp_attention_varlen", qkv.data_ptr(), 3 * C, 0, C, 2 * C, segs[0].data_ptr(),
                          segs[1].data_ptr(), nseg, mlen, H, D, bf, ao.data_ptr(), C)

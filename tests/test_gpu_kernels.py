@@ -353,15 +353,20 @@ def test_merge_filter_matches_oracle(lib):
     assert agree >= 0.995, agree
 
 
-@pytest.mark.parametrize("lens", [[500], [500, 325, 50, 128, 129], [25, 512, 257]])
-def test_attention_tcgen05(lib, lens):
+@pytest.mark.parametrize("qscale", [1.0, 6.0])
+@pytest.mark.parametrize("lens", [[500], [500, 325, 50, 128, 129], [25, 512, 257], [384, 1, 255, 256, 475]])
+def test_attention_tcgen05(lib, lens, qscale):
     """tcgen05 global attention (bf16 operands, fp32 softmax/accumulation) vs torch SDPA on the same
-    bf16-rounded q/k/v: tolerance 2e-2 absolute (bf16 P and bf16 output rounding)."""
+    bf16-rounded q/k/v: tolerance 2e-2 absolute (bf16 P and bf16 output rounding).  qscale 6 gives
+    scores of magnitude ~50, so the running maximum jumps between key blocks and the lazy rescale of
+    the O accumulator is exercised."""
     H, D = 8, 64
     C = H * D
     M = sum(lens)
     g = torch.Generator().manual_seed(M)
-    qkv = torch.randn(M, 3 * C, generator=g).to(torch.bfloat16)
+    qkv = torch.randn(M, 3 * C, generator=g)
+    qkv[:, :C] *= qscale
+    qkv = qkv.to(torch.bfloat16)
     out = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
     starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
     ds, dl = torch.as_tensor(starts).to(DEV), torch.as_tensor(np.asarray(lens, dtype=np.int32)).to(DEV)
@@ -378,21 +383,24 @@ def test_attention_tcgen05(lib, lens):
         assert err <= 2e-2, (n, err)
 
 
+@pytest.mark.parametrize("tiles", [1, 2, 4])
 @pytest.mark.parametrize("F", [1, 5, 13, 640])
-def test_attention_tcgen05_block_diagonal(lib, F):
-    """local attention: block-diagonal 25x25 blocks on 125-token tensor-core tiles vs per-block torch SDPA."""
+def test_attention_tcgen05_block_diagonal(lib, F, tiles):
+    """local attention: block-diagonal 25x25 blocks on 125-token tensor-core tiles (`tiles` tiles per CTA
+    segment) vs per-block torch SDPA."""
     H, D, L = 8, 64, 25
     C = H * D
     M = F * L
     g = torch.Generator().manual_seed(F)
     qkv = torch.randn(M, 3 * C, generator=g).to(torch.bfloat16)
     out = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
-    n = (F + 4) // 5
-    starts = (np.arange(n) * 125).astype(np.int32)
-    lens = np.minimum(125, M - starts).astype(np.int32)
+    per = 125 * tiles
+    n = (M + per - 1) // per
+    starts = (np.arange(n) * per).astype(np.int32)
+    lens = np.minimum(per, M - starts).astype(np.int32)
     ds, dl = torch.as_tensor(starts).to(DEV), torch.as_tensor(lens).to(DEV)
     dq = qkv.to(DEV)
-    lib.call("pfpp_attention_tc", dq.data_ptr(), M, 3 * C, C, ds.data_ptr(), dl.data_ptr(), n, 125, H, L, out.data_ptr(), C)
+    lib.call("pfpp_attention_tc", dq.data_ptr(), M, 3 * C, C, ds.data_ptr(), dl.data_ptr(), n, per, H, L, out.data_ptr(), C)
     torch.cuda.synchronize()
     o = out.cpu().float().view(F, L, C)
     q, k, v = [t.reshape(F, L, H, D).transpose(1, 2) for t in qkv.float().chunk(3, -1)]
