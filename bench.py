@@ -11,8 +11,10 @@ verifier pass (pose by-area clouds, edge histograms, verifier transformer, accep
   value : device-timed (CUDA events on the launch stream), inputs already resident in HBM
   e2e   : the same batch through the public call (run_batch on HOST tensors): H2D of every input
           and D2H of the predicted poses inside the timed region
-  roofline : the tcgen05 GEMM kernel, algorithmic FLOPs / CUDA-event time of its launches, measured
-          live in the timed region, against MEASURED_PEAKS.json (sustained bf16)
+  roofline : the tensor-core kernel with the largest share of the DDPM step (fused set abstraction, GEMM or
+          attention): algorithmic FLOPs / CUDA-event time of its launches against MEASURED_PEAKS.json
+          (sustained bf16), measured in an eager single-stream probe pass inside bench.py; `kernels` lists every
+          probed entry point (per-DDPM-step time, share, TFLOP/s)
   cpu_baseline : the oracle (CPU port of the reference path) on the host cores, bounded sample
 
 Multi-GPU (torchrun, one rank per GPU): objects are independent, so ranks run disjoint batches with
@@ -168,18 +170,45 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# per-launch event timing of the dominant kernel (tcgen05 GEMM)
+# per-launch event timing of the tensor-core kernels
 # ------------------------------------------------------------------------------------------------
-class GemmProbe:
-    """Wraps _lib.call: CUDA events around the pfpp_gemm_bf16 (or pfpp_gemm_f32) launches of the timed region.
+SA_LEVELS = {1: (32, 0, 64, 64, 128), 2: (64, 128, 128, 128, 256), 3: (64, 256, 256, 256, 512)}  # ns, D, C1, C2, C3
 
-    With CUDA-graph replay only the eagerly launched DDPM step of every batch step (the one that precedes
-    the capture) can carry events, so the kernel is SAMPLED there: every DDPM step launches the identical
-    GEMM sequence, hence average duration and FLOPs per launch are representative."""
 
-    def __init__(self, lib, name):
-        self.lib, self.name = lib, name
-        self.events, self.flops = [], 0.0
+def algorithmic_flops(name, args, latent_points=25, head_dim=64):
+    """Algorithmic FLOPs (2 per MAC; masked-out work not counted) of one launch, from its C-ABI arguments."""
+    if name == "pfpp_gemm_bf16":
+        M, N, K = args[10], args[11], args[12]
+        return 2.0 * M * N * K
+    if name == "pfpp_gemm_f32":
+        M, N, K = args[9], args[10], args[11]
+        return 2.0 * M * N * K
+    if name == "pfpp_sa_fused":
+        level, K, S = args[0], args[5], args[7]
+        ns, D, C1, C2, C3 = SA_LEVELS[level]
+        return 2.0 * K * S * ns * ((3 + D) * C1 + C1 * C2 + C2 * C3)
+    if name == "pfpp_attention_tc":
+        M, n_seg, max_len, heads, block = args[1], args[6], args[7], args[8], args[9]
+        if block:  # block-diagonal: every token attends to its own block
+            return 4.0 * M * block * head_dim * heads
+        return 4.0 * n_seg * max_len * max_len * head_dim * heads  # the bench's segments all have max_len tokens
+    return 0.0
+
+
+class KernelProbe:
+    """Wraps _lib.call with CUDA events around every launch of the probed entry points.
+
+    The timed region replays CUDA graphs on several streams, where per-kernel events cannot be placed (and
+    would time the other stream's kernels too); the probe therefore runs right after it, inside bench.py, on
+    the same warm engine: a few eagerly launched DDPM steps of the same batch on ONE stream, every probed
+    launch bracketed by events on that stream.  Every DDPM step launches the identical kernel sequence."""
+
+    NAMES = ("pfpp_gemm_bf16", "pfpp_gemm_f32", "pfpp_sa_fused", "pfpp_attention_tc", "pfpp_rotate_fps", "pfpp_fps",
+             "pfpp_ball_query", "pfpp_layernorm", "pfpp_vq")
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.rec = {}
         self.orig = lib.call
         self.enabled = False
 
@@ -187,26 +216,29 @@ class GemmProbe:
         probe = self
 
         def call(name, *args):
-            if probe.enabled and name == probe.name and not torch.cuda.is_current_stream_capturing():
+            if probe.enabled and name in probe.NAMES and not torch.cuda.is_current_stream_capturing():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 probe.orig(name, *args)
                 e1.record()
-                probe.events.append((e0, e1))
-                if name == "pfpp_gemm_bf16":
-                    M, N, K = args[10], args[11], args[12]
-                else:
-                    M, N, K = args[9], args[10], args[11]
-                probe.flops += 2.0 * M * N * K
+                r = probe.rec.setdefault(name, {"events": [], "flops": 0.0})
+                r["events"].append((e0, e1))
+                r["flops"] += algorithmic_flops(name, args)
             else:
                 probe.orig(name, *args)
         self.lib.call = call
         for m in modules:
             m.call = call
 
-    def result(self):
-        ms = sum(a.elapsed_time(b) for a, b in self.events)
-        return self.flops, ms, len(self.events)
+    def summary(self, ddpm_steps_probed):
+        out = {}
+        for name, r in self.rec.items():
+            ms = sum(a.elapsed_time(b) for a, b in r["events"])
+            n = len(r["events"])
+            out[name] = {"launches_per_ddpm_step": n / ddpm_steps_probed, "ms_per_ddpm_step": ms / ddpm_steps_probed,
+                         "avg_us": ms * 1e3 / max(n, 1),
+                         "tflops": (r["flops"] / (ms * 1e-3) / 1e12) if ms > 0 and r["flops"] else None}
+        return out
 
 
 def main():
@@ -240,8 +272,7 @@ def main():
     objects = [uniq[i % n_unique] for i in range(a.batch)]
     seeds = [rank * 10007 + i for i in range(a.batch)]
     parts = [list(range(i, a.batch, n_str)) for i in range(n_str)]  # object indices per stream
-    gemm_name = "pfpp_gemm_bf16" if a.precision == "bf16" else "pfpp_gemm_f32"
-    probe = GemmProbe(_lib, gemm_name)
+    probe = KernelProbe(_lib)
     probe.install([engine_mod, loop_mod, weights_mod])
 
     def make_states():
@@ -274,7 +305,6 @@ def main():
     states = [make_states() for _ in range(a.steps)]
     barrier()
     launches0 = _lib.launch_count
-    probe.enabled = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(None if a.no_clocks else local) as clk:
         e0.record()
@@ -282,7 +312,6 @@ def main():
             metrics = one_step(states[k])
         e1.record()
         barrier()
-    probe.enabled = False
     elapsed_ms = e0.elapsed_time(e1)
     launches = _lib.launch_count - launches0
     t = torch.tensor([elapsed_ms], device=dev)
@@ -307,7 +336,24 @@ def main():
         "part_pcs", "part_scale", "part_trans", "part_rots", "part_pcs_by_area"))
     d2h = a.batch * (20 * 7 * 4 * 2 + 190 * 4)
 
-    flops, gemm_ms, n_gemm = probe.result()
+    # ---- kernel probe: eager DDPM steps of the whole batch on one stream, events around every launch ----
+    probe_steps = 3
+    eng_p = Engine(ck, num_inference_steps=a.ddpm_steps, precision=a.precision, device=dev, chunk_frags=a.chunk)
+    runner = BatchRunner(eng_p, objects, max_iters=1, noise=PerObjectNoise(dev, seeds, a.ddpm_steps), trajectory=False,
+                         use_graph=False)
+    runner.begin_iteration()
+    runner._launch_step()  # sizes the workspaces
+    torch.cuda.synchronize()
+    probe.enabled = True
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(probe_steps):
+        runner._launch_step()
+    pe1.record()
+    torch.cuda.synchronize()
+    probe.enabled = False
+    probe_step_ms = pe0.elapsed_time(pe1) / probe_steps
+    kernels = probe.summary(probe_steps)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -319,10 +365,13 @@ def main():
     else:
         peak = 72.0  # fp32 FFMA nominal: 148 SM x 128 lanes x 2 x 1.9 GHz (no measured fp32 peak is provided)
         peak_src = "nominal fp32 FFMA"
-    achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    # sampled launches belong to eagerly launched DDPM steps; scale to all DDPM steps of a batch step
-    sampled_ddpm_steps = a.steps * n_str * (1 if not a.no_graph else a.ddpm_steps)
-    gemm_ms_per_step = gemm_ms / max(sampled_ddpm_steps, 1) * a.ddpm_steps * n_str
+    tensor_kernels = {k: v for k, v in kernels.items() if v["tflops"]}
+    dom = max(tensor_kernels, key=lambda k: tensor_kernels[k]["ms_per_ddpm_step"])
+    for v in kernels.values():
+        v["share_of_ddpm_step"] = v["ms_per_ddpm_step"] / probe_step_ms
+        v["frac_of_peak"] = (v["tflops"] / peak) if v["tflops"] else None
+    step_flops = sum(v["tflops"] * 1e12 * v["ms_per_ddpm_step"] * 1e-3 for v in tensor_kernels.values())
+    ddpm_ms_timed = elapsed_ms / a.steps / a.ddpm_steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -332,12 +381,16 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clk.summary(),
-        "roofline": {"bound": "tensor", "kernel": gemm_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
-                     "launches_sampled": n_gemm, "kernel_ms_per_step": gemm_ms_per_step,
-                     "share_of_step": gemm_ms_per_step / (elapsed_ms / a.steps) if elapsed_ms else None,
-                     "note": "algorithmic FLOPs (2MNK) of the sampled launches / their CUDA-event time; with >1 "
-                             "stream the event time includes kernels of the other stream running concurrently"},
+        "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
+                     "frac": kernels[dom]["tflops"] / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "avg_launch_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["share_of_ddpm_step"],
+                     "whole_step": {"algorithmic_tflop_per_ddpm_step": step_flops / 1e12,
+                                    "achieved_tflops_timed_region": step_flops / (ddpm_ms_timed * 1e-3) / 1e12,
+                                    "frac_of_peak": step_flops / (ddpm_ms_timed * 1e-3) / 1e12 / peak},
+                     "note": "dominant kernel = largest share of the DDPM step; per-launch CUDA events in an eager "
+                             "single-stream probe pass inside bench.py right after the timed region (the timed region "
+                             "replays CUDA graphs); FLOPs are algorithmic (masked work not counted)"},
+        "kernels": kernels,
     }
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:

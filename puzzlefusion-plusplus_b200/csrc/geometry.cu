@@ -86,14 +86,23 @@ extern "C" int pfpp_pose_apply(const float* pts, const int* seg_start, const int
 // ---------------------------------------------------------------------------------------------
 #define FPS_THREADS 256
 
-struct FpsBest {
-  float d;
-  int key;  // (owner thread << 20) | point index ; smaller wins on equal d
-};
-
-__device__ __forceinline__ FpsBest fps_better(FpsBest a, FpsBest b) {
-  bool take_b = (b.d > a.d) || (b.d == a.d && b.key < a.key);
-  return take_b ? b : a;
+// Block-wide arg-max of (distance, then lower owner thread, then lower point index) with two warp-level
+// redux.sync passes instead of shuffle trees.  Distances are >= 0, so their bit patterns order like
+// unsigned integers; `ud` = bits + 1, with 0 reserved for "this thread owns no point".  Within a thread the
+// caller keeps the first (lowest-index) maximum; between lanes / warps the lowest one wins, which is the
+// (lower thread, lower index) tie-break of torch_cluster's strided scan + tree reduce.
+// red_d / red_k: [2][FPS_THREADS/32] double-buffered partials -> one barrier per round.
+__device__ __forceinline__ int fps_block_argmax(unsigned ud, int n, int par, unsigned (*red_d)[FPS_THREADS / 32],
+                                                int (*red_k)[FPS_THREADS / 32], int lane, int warp) {
+  const unsigned m = __reduce_max_sync(0xffffffffu, ud);
+  const unsigned win = __ballot_sync(0xffffffffu, ud == m);
+  if (lane == __ffs(win) - 1) red_d[par][warp] = m, red_k[par][warp] = n;
+  __syncthreads();
+  const unsigned pd = lane < FPS_THREADS / 32 ? red_d[par][lane] : 0u;
+  const int pk = lane < FPS_THREADS / 32 ? red_k[par][lane] : 0;
+  const unsigned m2 = __reduce_max_sync(0xffffffffu, pd);
+  const unsigned win2 = __ballot_sync(0xffffffffu, pd == m2 && lane < FPS_THREADS / 32);
+  return __shfl_sync(0xffffffffu, pk, __ffs(win2) - 1);
 }
 
 template <int PPT, bool ROTATE>
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(FPS_THREADS)
   float* sx = sm;
   float* sy = sm + N;
   float* sz = sm + 2 * N;
-  __shared__ float red_d[2][FPS_THREADS / 32];
+  __shared__ unsigned red_d[2][FPS_THREADS / 32];
   __shared__ int red_k[2][FPS_THREADS / 32];
 
   const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,7 +158,8 @@ __global__ void __launch_bounds__(FPS_THREADS)
       if (ox) ox[3 * m] = cx, ox[3 * m + 1] = cy, ox[3 * m + 2] = cz;
     }
     if (m + 1 == S) break;
-    FpsBest best{-1.0f, 0};
+    unsigned bd = 0u;  // best of this thread's points: distance bits + 1 (0 = none), first maximum wins
+    int bn = 0;
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
       int n = tid + i * FPS_THREADS;
@@ -158,21 +168,11 @@ __global__ void __launch_bounds__(FPS_THREADS)
         float dd = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
         dd = fminf(dist[i], dd);
         dist[i] = dd;
-        if (dd > best.d) best = FpsBest{dd, (tid << 20) | n};
+        const unsigned u = __float_as_uint(dd) + 1u;
+        if (u > bd) bd = u, bn = n;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      FpsBest other{__shfl_xor_sync(0xffffffffu, best.d, o), __shfl_xor_sync(0xffffffffu, best.key, o)};
-      best = fps_better(best, other);
-    }
-    const int par = m & 1;  // double-buffered partials: one barrier per round
-    if (lane == 0) red_d[par][warp] = best.d, red_k[par][warp] = best.key;
-    __syncthreads();
-    FpsBest b{red_d[par][0], red_k[par][0]};
-#pragma unroll
-    for (int w = 1; w < FPS_THREADS / 32; ++w) b = fps_better(b, FpsBest{red_d[par][w], red_k[par][w]});
-    cur = b.key & 0xFFFFF;
+    cur = fps_block_argmax(bd, bn, m & 1, red_d, red_k, lane, warp);
   }
 }
 
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(FPS_THREADS)
                      const int* __restrict__ cloud_len, const int* __restrict__ n_samples,
                      const int* __restrict__ start, float* __restrict__ dist, const int* __restrict__ out_start,
                      int* __restrict__ out_idx) {
-  __shared__ float red_d[2][FPS_THREADS / 32];
+  __shared__ unsigned red_d[2][FPS_THREADS / 32];
   __shared__ int red_k[2][FPS_THREADS / 32];
   const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = cloud_len[k], S = n_samples[k];
@@ -195,26 +195,17 @@ __global__ void __launch_bounds__(FPS_THREADS)
     if (tid == 0) oi[m] = cur;
     if (m + 1 == S) break;
     float cx = p[3 * cur], cy = p[3 * cur + 1], cz = p[3 * cur + 2];
-    FpsBest best{-1.0f, 0};
+    unsigned bd = 0u;
+    int bn = 0;
     for (int n = tid; n < N; n += FPS_THREADS) {
       float dx = fsub(cx, p[3 * n]), dy = fsub(cy, p[3 * n + 1]), dz = fsub(cz, p[3 * n + 2]);
       float dd = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
       dd = fminf(d[n], dd);
       d[n] = dd;
-      if (dd > best.d) best = FpsBest{dd, (tid << 20) | n};
+      const unsigned u = __float_as_uint(dd) + 1u;
+      if (u > bd) bd = u, bn = n;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      FpsBest other{__shfl_xor_sync(0xffffffffu, best.d, o), __shfl_xor_sync(0xffffffffu, best.key, o)};
-      best = fps_better(best, other);
-    }
-    const int par = m & 1;
-    if (lane == 0) red_d[par][warp] = best.d, red_k[par][warp] = best.key;
-    __syncthreads();
-    FpsBest b{red_d[par][0], red_k[par][0]};
-#pragma unroll
-    for (int w = 1; w < FPS_THREADS / 32; ++w) b = fps_better(b, FpsBest{red_d[par][w], red_k[par][w]});
-    cur = b.key & 0xFFFFF;
+    cur = fps_block_argmax(bd, bn, m & 1, red_d, red_k, lane, warp);
   }
 }
 

@@ -19,6 +19,7 @@
 // Layer 0 is split: the D feature columns go through the tensor cores (aligned 16-byte gathers), the three
 // centroid-offset columns (dx,dy,dz) are added in the epilogue as fp32 FMAs by the thread that owns the row
 // -- exact fp32 geometry terms, no padded K panel, and the first level (D = 0) needs no layer-0 MMA at all.
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -429,14 +430,28 @@ extern "C" int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, 
   if (K == 0) return PFPP_OK;
   SaParams p{xyz, new_xyz, (const __nv_bfloat16*)feats, gidx, w0_xyz, b0, b1, b2, (__nv_bfloat16*)out, N, S,
              (long long)K * S};
+  // PFPP_SA_VARIANT (tuning aid, tools/bench_sa.py): depth of the weight ring per level
+  static const int variant = []() {
+    const char* e = getenv("PFPP_SA_VARIANT");
+    return e ? atoi(e) : 0;
+  }();
   switch (level) {
     case 1:
+      if (variant == 1) return launch_sa<32, 0, 64, 64, 128, 4, 1>(p, w0_feat, w1, w2, stream);
       return launch_sa<32, 0, 64, 64, 128, 2, 1>(p, w0_feat, w1, w2, stream);
     case 2:
       PFPP_CHECK_ARG(feats && w0_feat);
+      if (variant == 1) return launch_sa<64, 128, 128, 128, 256, 4, 2>(p, w0_feat, w1, w2, stream);
+      if (variant == 2) return launch_sa<64, 128, 128, 128, 256, 6, 2>(p, w0_feat, w1, w2, stream);
+      if (variant == 3) return launch_sa<64, 128, 128, 128, 256, 2, 1>(p, w0_feat, w1, w2, stream);
+      if (variant == 4) return launch_sa<64, 128, 128, 128, 256, 3, 1>(p, w0_feat, w1, w2, stream);
       return launch_sa<64, 128, 128, 128, 256, 2, 2>(p, w0_feat, w1, w2, stream);
     case 3:
       PFPP_CHECK_ARG(feats && w0_feat);
+      if (variant == 1) return launch_sa<64, 256, 256, 256, 512, 4, 2>(p, w0_feat, w1, w2, stream);
+      if (variant == 2) return launch_sa<64, 256, 256, 256, 512, 5, 2>(p, w0_feat, w1, w2, stream);
+      if (variant == 3) return launch_sa<64, 256, 256, 256, 512, 2, 1>(p, w0_feat, w1, w2, stream);
+      if (variant == 4) return launch_sa<64, 256, 256, 256, 512, 3, 1>(p, w0_feat, w1, w2, stream);
       return launch_sa<64, 256, 256, 256, 512, 2, 2>(p, w0_feat, w1, w2, stream);
     default:
       return PFPP_EINVAL;

@@ -146,18 +146,23 @@ __global__ void __launch_bounds__(256)
   const float* md = mod ? mod + (size_t)row_group[row / rows_per_group] * 2 * C : nullptr;
 #pragma unroll
   for (int i = 0; i < PER; i += 4) {
-    int c = (i / 4) * 128 + lane * 4;
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float n = (v[i + j] - mean) * rstd;
-      if (md) n = n * (1.0f + md[c + j]) + md[C + c + j];
-      else if (gamma) n = n * gamma[c + j] + beta[c + j];
-      o[j] = n;
+    const int c = (i / 4) * 128 + lane * 4;
+    float o[4] = {(v[i] - mean) * rstd, (v[i + 1] - mean) * rstd, (v[i + 2] - mean) * rstd, (v[i + 3] - mean) * rstd};
+    if (md) {
+      const float4 sc = *reinterpret_cast<const float4*>(md + c), sh = *reinterpret_cast<const float4*>(md + C + c);
+      o[0] = o[0] * (1.0f + sc.x) + sh.x, o[1] = o[1] * (1.0f + sc.y) + sh.y;
+      o[2] = o[2] * (1.0f + sc.z) + sh.z, o[3] = o[3] * (1.0f + sc.w) + sh.w;
+    } else if (gamma) {
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+      o[0] = o[0] * ga.x + be.x, o[1] = o[1] * ga.y + be.y, o[2] = o[2] * ga.z + be.z, o[3] = o[3] * ga.w + be.w;
     }
     OutT* yo = y + row * C + c;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) yo[j] = cvt_out<OutT>(o[j]);
+    if (sizeof(OutT) == 2) {  // bf16: one 8-byte store per lane
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+      *reinterpret_cast<uint2*>(yo) = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+    } else {
+      *reinterpret_cast<float4*>(yo) = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 

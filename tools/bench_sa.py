@@ -1,0 +1,49 @@
+"""Time the fused set-abstraction kernel per level on the bench shape (640 fragments).
+
+usage: [PFPP_SA_VARIANT=v] bench_sa.py [fragments] [reps]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from puzzlefusion_plusplus_b200 import _lib  # noqa: E402
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 640
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+dev = "cuda:0"
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+# (level, N, S, NS, D, C1, C2, C3)
+LEVELS = [(1, 1000, 256, 32, 0, 64, 64, 128), (2, 256, 128, 64, 128, 128, 128, 256), (3, 128, 25, 64, 256, 256, 256, 512)]
+for level, N, S, NS, D, C1, C2, C3 in LEVELS:
+    g = torch.Generator(device=dev).manual_seed(level)
+    xyz = torch.rand(K, N, 3, device=dev, generator=g)
+    new_xyz = torch.rand(K, S, 3, device=dev, generator=g)
+    feats = torch.randn(K, N, max(D, 1), device=dev, generator=g).to(torch.bfloat16)
+    gidx = torch.randint(0, N, (K, S, NS), device=dev, generator=g, dtype=torch.int32)
+    w0 = (torch.randn(C1, max(D, 8), device=dev, generator=g) * 0.05).to(torch.bfloat16)
+    wxyz = torch.randn(C1, 4, device=dev, generator=g)
+    w1 = (torch.randn(C2, C1, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+    w2 = (torch.randn(C3, C2, device=dev, generator=g) * 0.05).to(torch.bfloat16)
+    b0, b1, b2 = [torch.randn(c, device=dev, generator=g) * 0.1 for c in (C1, C2, C3)]
+    out = torch.empty(K * S, C3, device=dev, dtype=torch.bfloat16)
+
+    def fn():
+        _lib.call("pfpp_sa_fused", level, xyz.data_ptr(), new_xyz.data_ptr(), feats.data_ptr() if D else None, gidx.data_ptr(),
+                  K, N, S, w0.data_ptr() if D else None, wxyz.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(),
+                  w2.data_ptr(), b2.data_ptr(), out.data_ptr())
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    us = float(np.median(ts))
+    flops = 2.0 * K * S * NS * ((3 + D) * C1 + C1 * C2 + C2 * C3)
+    print(f"level {level}: {us:8.1f} us   {flops / us / 1e6:7.1f} TFLOP/s   checksum {out.float().sum().item():.4e}")
