@@ -95,6 +95,10 @@ int pfpp_vq(const void* z, int z_is_bf16, long long n_chunks, const float* codeb
 int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K, int N,
                   int S, const void* w0_feat, const float* w0_xyz, const float* b0, const void* w1, const float* b1,
                   const void* w2, const float* b2, void* out, cudaStream_t stream);
+/* debug variant of pfpp_sa_fused: per-CTA clock stamps of the kernel phases into trace[grid][16] */
+int pfpp_sa_fused_trace(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K, int N,
+                  int S, const void* w0_feat, const float* w0_xyz, const float* b0, const void* w1, const float* b1,
+                  const void* w2, const float* b2, void* out, long long* trace, cudaStream_t stream);
 
 /* ---- contractions ---------------------------------------------------------------------- */
 

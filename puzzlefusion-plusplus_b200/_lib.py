@@ -30,6 +30,7 @@ SIGNATURES = {
     "pfpp_group_gather": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "pfpp_group_max": [_P, _L, _I, _I, _I, _I, _P, _I, _P],
     "pfpp_sa_fused": [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "pfpp_sa_fused_trace": [_I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pfpp_vq": [_P, _I, _L, _P, _I, _P, _P, _P],
     "pfpp_gemm_f32": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "pfpp_gemm_bf16": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -111,6 +111,7 @@ struct SaParams {
   __nv_bfloat16* out;      // [K*S, C3]
   int N, S;
   long long groups;        // K * S
+  long long* trace;        // debug: per-CTA clock64 stamps [grid][16] (nullptr in the product path)
 };
 
 template <int NS, int D, int C1, int C2, int C3, int STAGES, int SUB>
@@ -194,6 +195,11 @@ __global__ void __launch_bounds__(128 * SUB + 32)
   }
 
 #define SA_BAR() asm volatile("bar.sync 1, %0;" ::"n"(Cfg::ROWS) : "memory")
+#define SA_TRACE(slot)                                                                  \
+  do {                                                                                 \
+    if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+  } while (0)
+  SA_TRACE(0);
 
   float d3[3] = {0.f, 0.f, 0.f};  // this thread's row: xyz[idx] - centroid (fp32, used by the layer-0 epilogue)
   // ---------------- gather: X0[row] = feats[idx] (bf16, swizzled) ----------
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(128 * SUB + 32)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   SA_BAR();
+  SA_TRACE(1);
 
   int w_it = 0;  // consumer position in the weight ring (thread 32 only)
   uint32_t acc_phase = 0;
@@ -290,6 +297,7 @@ __global__ void __launch_bounds__(128 * SUB + 32)
       acc_phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    SA_TRACE(2 + 2 * layer);
     // epilogue: thread = row; (+ xyz terms) + bias + ReLU -> bf16 -> next operand tile (in place)
     const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16) + sub * Cfg::CW;
 #pragma unroll 1
@@ -324,6 +332,7 @@ __global__ void __launch_bounds__(128 * SUB + 32)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     SA_BAR();
+    SA_TRACE(3 + 2 * layer);
   }
 
   // ---------------- layer 2: channels on M (one 128-channel block at a time), rows on N ----------------
@@ -353,6 +362,7 @@ __global__ void __launch_bounds__(128 * SUB + 32)
       mbar_wait(bar_acc, acc_phase);
       acc_phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (mb < 4) SA_TRACE(6 + 2 * mb);
       const int ch = mb * 128 + wq * 32 + lane;
       const float bias = b2s[ch];
 #pragma unroll 1
@@ -372,10 +382,13 @@ __global__ void __launch_bounds__(128 * SUB + 32)
       // the next channel block reuses the same TMEM columns: every compute warp must have drained them
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       SA_BAR();
+      if (mb < 4) SA_TRACE(7 + 2 * mb);
     }
   }
+  SA_TRACE(14);
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS));
 #undef SA_BAR
+#undef SA_TRACE
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
@@ -423,13 +436,14 @@ int launch_sa(const SaParams& p, const void* w0, const void* w1, const void* w2,
 
 }  // namespace
 
-extern "C" int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K,
-                             int N, int S, const void* w0_feat, const float* w0_xyz, const float* b0, const void* w1,
-                             const float* b1, const void* w2, const float* b2, void* out, cudaStream_t stream) {
+static int sa_dispatch(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K,
+                       int N, int S, const void* w0_feat, const float* w0_xyz, const float* b0, const void* w1,
+                       const float* b1, const void* w2, const float* b2, void* out, long long* trace,
+                       cudaStream_t stream) {
   PFPP_CHECK_ARG(xyz && new_xyz && gidx && w0_xyz && w1 && w2 && b0 && b1 && b2 && out && K >= 0);
   if (K == 0) return PFPP_OK;
   SaParams p{xyz, new_xyz, (const __nv_bfloat16*)feats, gidx, w0_xyz, b0, b1, b2, (__nv_bfloat16*)out, N, S,
-             (long long)K * S};
+             (long long)K * S, trace};
   // PFPP_SA_VARIANT (tuning aid, tools/bench_sa.py): depth of the weight ring per level
   static const int variant = []() {
     const char* e = getenv("PFPP_SA_VARIANT");
@@ -456,4 +470,18 @@ extern "C" int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, 
     default:
       return PFPP_EINVAL;
   }
+}
+
+extern "C" int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K,
+                             int N, int S, const void* w0_feat, const float* w0_xyz, const float* b0, const void* w1,
+                             const float* b1, const void* w2, const float* b2, void* out, cudaStream_t stream) {
+  return sa_dispatch(level, xyz, new_xyz, feats, gidx, K, N, S, w0_feat, w0_xyz, b0, w1, b1, w2, b2, out, nullptr, stream);
+}
+
+// Debug variant: per-CTA clock64 stamps of the kernel phases into trace[grid][16] (tools/bench_sa.py --trace).
+extern "C" int pfpp_sa_fused_trace(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx,
+                                   int K, int N, int S, const void* w0_feat, const float* w0_xyz, const float* b0,
+                                   const void* w1, const float* b1, const void* w2, const float* b2, void* out,
+                                   long long* trace, cudaStream_t stream) {
+  return sa_dispatch(level, xyz, new_xyz, feats, gidx, K, N, S, w0_feat, w0_xyz, b0, w1, b1, w2, b2, out, trace, stream);
 }

@@ -222,3 +222,23 @@ def test_fused_sa_matches_unfused(engines, ckpt):
         err_f, err_u = (a - o).abs().max() / scale, (b - o).abs().max() / scale
         assert err_f <= 3e-2, (lvl, err_f)
         assert err_f <= 1.5 * err_u + 5e-3, (lvl, err_f, err_u)
+
+
+def test_stress_shape_config5_vs_oracle():
+    """BASELINE config 5 shape (64 valid fragments x 2000 points, PE tables extended to 64 slots; 3 DDPM steps
+    of the 250-step schedule): 1600-token global attention segments, 8 points per FPS thread.  fp32 mode
+    within 1e-4 of the oracle, bf16 mode within 5e-2 (same tolerances as the small-shape loop tests)."""
+    from puzzlefusion_plusplus_b200 import synthetic
+    from puzzlefusion_plusplus_b200.engine import Engine
+    from puzzlefusion_plusplus_b200.loop import ReplayNoise, run_batch
+    P = 64
+    ck = synthetic.make_checkpoints(0, max_parts=P)
+    obj = synthetic.make_object(77, num_parts=P, n_points=2000, max_parts=P)
+    gen = torch.Generator().manual_seed(5)
+    normals = [torch.randn(1, P, 7, generator=gen) for _ in range(4)]
+    res = ol.run_object(ck["encoder"], ck["denoiser"], ck["verifier"], obj, 3, 1, rng=ol.ReplayRNG(normals))
+    for precision, tol in (("fp32", 1e-4), ("bf16", 5e-2)):
+        eng = Engine(ck, num_inference_steps=3, precision=precision, device=DEV, max_parts=P)
+        out = run_batch(eng, [obj], max_iters=1, noise=ReplayNoise(normals, [], DEV))
+        err = (out["x"][0] - res["x"]).abs().max().item()
+        assert err <= tol, (precision, err)
