@@ -16,9 +16,14 @@
 // layer boundaries; X tiles are written by the CTA's own threads (generic proxy) and published to the
 // tensor core with fence.proxy.async.
 //
-// Layer 0 is split: the D feature columns go through the tensor cores (aligned 16-byte gathers), the three
-// centroid-offset columns (dx,dy,dz) are added in the epilogue as fp32 FMAs by the thread that owns the row
-// -- exact fp32 geometry terms, no padded K panel, and the first level (D = 0) needs no layer-0 MMA at all.
+// Layer 0 is split: the D feature columns go through the tensor cores as 64-wide K panels (aligned 16-byte
+// gathers); the three centroid-offset columns (dx,dy,dz) go through ONE extra K=16 MMA step on a small
+// un-swizzled operand that holds each offset and each weight as a bf16 hi/lo pair:
+//     w.d ~= w_hi d_hi + w_hi d_lo + w_lo d_hi        (9 of the 16 K slots; the products are exact in the fp32
+// accumulator, the dropped w_lo d_lo term is 2^-16 relative) -- fp32-grade geometry terms without the 256
+// broadcast LDS.128 per row that an epilogue FMA formulation costs (that epilogue was bound by shared-memory
+// return bandwidth).
+#include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -90,6 +95,19 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+// K-major, no swizzle: core matrix = 8 rows x 16 B stored contiguously; [rows x 16] bf16 operand laid out as
+// (row / 8) * 256 + (k / 8) * 128 + (row % 8) * 16 + (k % 8) * 2   ->  LBO (next core matrix in K) = 128 B,
+// SBO (next 8-row group) = 256 B
+__device__ __forceinline__ uint64_t desc_kmajor_nosw(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ uint32_t xyzoff(int row, int kchunk) {
+  return (uint32_t)(row >> 3) * 256u + (uint32_t)kchunk * 128u + (uint32_t)(row & 7) * 16u;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 // D=f32, A=B=bf16, both K-major, M=128, N=128
 constexpr uint32_t SF_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
@@ -104,7 +122,7 @@ struct SaParams {
   const float* new_xyz;    // [K, S, 3] centroids
   const __nv_bfloat16* feats;  // [K, N, D] previous level features (nullptr when D == 0)
   const int* gidx;         // [K, S, NS]
-  const float* wxyz;       // [C1, 4] fp32: layer-0 weights of the (dx,dy,dz) columns, applied in the epilogue
+  const float* wxyz;       // [C1, 4] fp32: layer-0 weights of the (dx,dy,dz) columns
   const float* b0;
   const float* b1;
   const float* b2;
@@ -127,19 +145,26 @@ struct SaCfg {
   static constexpr uint32_t OFF_X = 0;
   static constexpr uint32_t OFF_W = SUB * X_BYTES;
   static constexpr uint32_t OFF_BAR = OFF_W + STAGES * SF_TILE;
-  static constexpr uint32_t OFF_ROWS = OFF_BAR + 128;        // [ROWS] int64 gather offsets
-  static constexpr uint32_t OFF_CONST = OFF_ROWS + 8 * ROWS; // wxyz [C1][4] | b0 [C1] | b1 [C2] | b2 [C3]  (fp32)
-  static constexpr uint32_t CONST_BYTES = (C1 * 5 + C2 + C3) * 4;
+  static constexpr uint32_t OFF_ROWS = OFF_BAR + 128;        // [ROWS] int32 gather offsets
+  static constexpr uint32_t OFF_XYZ = OFF_ROWS + 4 * ROWS;   // [SUB][128 rows x 16] bf16 hi/lo offsets (un-swizzled operand)
+  static constexpr int WXYZ_ROWS = ((C1 + 127) / 128) * 128;
+  static constexpr uint32_t OFF_WXYZ = OFF_XYZ + SUB * 4096; // [WXYZ_ROWS x 16] bf16 hi/lo weights of (dx,dy,dz)
+  static constexpr uint32_t OFF_CONST = OFF_WXYZ + WXYZ_ROWS * 32;  // b0 [C1] | b1 [C2] | b2 [C3]  (fp32)
+  static constexpr uint32_t CONST_BYTES = (C1 + C2 + C3) * 4;
   static constexpr uint32_t SMEM = OFF_CONST + CONST_BYTES + 1024 /*align slack*/;
   static constexpr int CW = (NB1 > NB2 ? NB1 : NB2) * 128;  // TMEM columns per sub-tile in layers 0/1
   static constexpr int TMEM_NEED = SUB * (CW > 128 ? CW : 128);
   static constexpr int TMEM_COLS = TMEM_NEED > 256 ? 512 : (TMEM_NEED > 128 ? 256 : 128);
+  // CTAs that can share an SM (shared memory and TMEM bound): the register budget is set to allow them
+  static constexpr int BY_SMEM = (227 * 1024) / (int)(SMEM + 1024);
+  static constexpr int BY_TMEM = 512 / TMEM_COLS;
+  static constexpr int MINB = BY_SMEM < BY_TMEM ? (BY_SMEM < 1 ? 1 : BY_SMEM) : BY_TMEM;
   static constexpr int GS = 128 / NS;                       // groups per sub-tile
   static constexpr int G = GS * SUB;                        // groups per CTA
 };
 
 template <int NS, int D, int C1, int C2, int C3, int STAGES, int SUB>
-__global__ void __launch_bounds__(128 * SUB + 32)
+__global__ void __launch_bounds__(128 * SUB + 32, SaCfg<NS, D, C1, C2, C3, STAGES, SUB>::MINB)
     sa_fused_kernel(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
                     const __grid_constant__ CUtensorMap map_w2, const SaParams p) {
   using Cfg = SaCfg<NS, D, C1, C2, C3, STAGES, SUB>;
@@ -152,7 +177,7 @@ __global__ void __launch_bounds__(128 * SUB + 32)
   const uint32_t tmem_slot = bar_acc + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = warp >> 2, wq = warp & 3;                  // sub-tile and TMEM lane quarter of a compute warp
-  const long long g0 = (long long)blockIdx.x * Cfg::G;
+  const long long n_tiles = (p.groups + Cfg::G - 1) / Cfg::G;  // persistent CTA: tiles blockIdx.x, + gridDim.x, ...
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -184,13 +209,19 @@ __global__ void __launch_bounds__(128 * SUB + 32)
       tma_load_2d(base + Cfg::OFF_W + s * SF_TILE, m, bar_full + 8 * s, kcol, row);
       ++it;
     };
-    if (D > 0)
-      for (int nb = 0; nb < Cfg::NB1; ++nb)
-        for (int kp = 0; kp < Cfg::P0; ++kp) push(&map_w0, kp * 64, nb * 128);
-    for (int nb = 0; nb < Cfg::NB2; ++nb)
-      for (int kp = 0; kp < Cfg::P1; ++kp) push(&map_w1, kp * 64, nb * 128);
-    for (int mb = 0; mb < Cfg::MB3; ++mb)
-      for (int kp = 0; kp < Cfg::P2; ++kp) push(&map_w2, kp * 64, mb * 128);
+    // RESIDENT: a tile's weights fill the ring exactly once (level 1: 2 tiles), so they are loaded for the first
+    // tile only and stay in shared memory for every later tile of this CTA
+    constexpr int TOT = (D > 0 ? Cfg::NB1 * Cfg::P0 : 0) + Cfg::NB2 * Cfg::P1 + Cfg::MB3 * Cfg::P2;
+    constexpr bool RESIDENT = TOT == STAGES;
+    for (long long tile = blockIdx.x; tile < (RESIDENT ? (long long)blockIdx.x + 1 : n_tiles); tile += gridDim.x) {
+      if (D > 0)
+        for (int nb = 0; nb < Cfg::NB1; ++nb)
+          for (int kp = 0; kp < Cfg::P0; ++kp) push(&map_w0, kp * 64, nb * 128);
+      for (int nb = 0; nb < Cfg::NB2; ++nb)
+        for (int kp = 0; kp < Cfg::P1; ++kp) push(&map_w1, kp * 64, nb * 128);
+      for (int mb = 0; mb < Cfg::MB3; ++mb)
+        for (int kp = 0; kp < Cfg::P2; ++kp) push(&map_w2, kp * 64, mb * 128);
+    }
     return;  // the ring drains on its own; shared memory stays live until the compute warps exit
   }
 
@@ -201,68 +232,101 @@ __global__ void __launch_bounds__(128 * SUB + 32)
   } while (0)
   SA_TRACE(0);
 
-  float d3[3] = {0.f, 0.f, 0.f};  // this thread's row: xyz[idx] - centroid (fp32, used by the layer-0 epilogue)
+  {  // per-channel constants -> shared memory once per CTA
+    float* cst = reinterpret_cast<float*>(bp + Cfg::OFF_CONST);
+    for (int i = threadIdx.x; i < C1; i += Cfg::ROWS) cst[i] = p.b0[i];
+    for (int i = threadIdx.x; i < C2; i += Cfg::ROWS) cst[C1 + i] = p.b1[i];
+    for (int i = threadIdx.x; i < C3; i += Cfg::ROWS) cst[C1 + C2 + i] = p.b2[i];
+    // weight side of the (dx,dy,dz) K=16 step: k = [x_hi y_hi z_hi | x_hi y_hi z_hi | x_lo y_lo z_lo | 0 ...]
+    for (int n = threadIdx.x; n < Cfg::WXYZ_ROWS; n += Cfg::ROWS) {
+      float w[3] = {0.f, 0.f, 0.f}, hi[3], lo[3];
+      if (n < C1) w[0] = p.wxyz[n * 4], w[1] = p.wxyz[n * 4 + 1], w[2] = p.wxyz[n * 4 + 2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        hi[i] = __bfloat162float(__float2bfloat16_rn(w[i]));
+        lo[i] = w[i] - hi[i];
+      }
+      uint8_t* wb = bp + Cfg::OFF_WXYZ;
+      *reinterpret_cast<uint4*>(wb + xyzoff(n, 0)) =
+          make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[0]), pack_bf16(hi[1], hi[2]), pack_bf16(lo[0], lo[1]));
+      *reinterpret_cast<uint4*>(wb + xyzoff(n, 1)) = make_uint4(pack_bf16(lo[2], 0.f), 0u, 0u, 0u);
+    }
+  }
+  // Weight-ring bookkeeping: a tile consumes RING_TOT stages = RING_ROUNDS whole trips around the ring, so the
+  // stage index of every load is a compile-time constant inside a tile (w_it restarts at 0) and only the phase
+  // parity carries over from tile to tile (ring_par).  Keeping w_it itself as a loop-carried runtime counter
+  // costs ~60 registers (every unrolled MMA descriptor becomes an address computation), i.e. a resident CTA.
+  constexpr int RING_TOT = (D > 0 ? Cfg::NB1 * Cfg::P0 : 0) + Cfg::NB2 * Cfg::P1 + Cfg::MB3 * Cfg::P2;
+  static_assert(RING_TOT % STAGES == 0, "a tile must consume whole trips around the weight ring");
+  constexpr int RING_ROUNDS = RING_TOT / STAGES;
+  constexpr bool RESIDENT = RING_TOT == STAGES;  // weights stay in the ring after the first tile (see the producer)
+  uint32_t ring_par = 0;
+  constexpr int ACC_USES = 2 + Cfg::MB3;  // bar_acc completions per tile
+  uint32_t acc_par = 0;  // phase parity of bar_acc at the start of the tile (flips per tile when ACC_USES is odd)
+  const float* cst = reinterpret_cast<const float*>(bp + Cfg::OFF_CONST);
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const long long g0 = tile * Cfg::G;
+  const bool tr0 = tile == blockIdx.x;  // trace stamps: first tile only
+  int w_it = 0;  // consumer position in the weight ring within this tile (thread 32 only)
+  uint32_t acc_phase = 0;
+  // re-derived per tile behind an opaque barrier: otherwise the compiler hoists every swizzled operand address
+  // of the epilogues out of the tile loop and keeps ~60 of them live in registers (which costs a resident CTA)
+  int row = wq * 32 + lane;                                            // row inside this thread's sub-tile
+  asm volatile("" : "+r"(row));
+  uint8_t* xsub = bp + Cfg::OFF_X + sub * Cfg::X_BYTES;                // this sub-tile's operand buffer
   // ---------------- gather: X0[row] = feats[idx] (bf16, swizzled) ----------
   // phase 1: thread = row -> neighbour index, xyz offset; phase 2: all threads stream the feature rows as
-  // 16-byte chunks (consecutive threads = consecutive chunks of a row), 8 loads in flight per thread.
+  // 16-byte cp.async chunks (consecutive threads = consecutive chunks of a row) straight into the swizzled
+  // operand tile, every chunk of the tile in flight at once.
   {
-    long long* src_row = reinterpret_cast<long long*>(bp + Cfg::OFF_ROWS);  // element offsets, -1 = padding
+    int* src_row = reinterpret_cast<int*>(bp + Cfg::OFF_ROWS);  // source point index in [0, K*N), -1 = padding
     {
       const int r = threadIdx.x;  // 0 .. ROWS-1
       const long long g = g0 + r / NS;
       const bool valid = g < p.groups;
-      long long off = -1;
+      int off = -1;
+      float d[3] = {0.f, 0.f, 0.f}, hi[3], lo[3];  // this row: xyz[idx] - centroid (fp32), then its bf16 hi/lo split
       if (valid) {
         const int idx = p.gidx[g * NS + (r % NS)];
-        const long long k = g / p.S;
-        off = k * p.N + idx;
-        const float* px = p.xyz + off * 3;
+        off = (int)(g / p.S) * p.N + idx;
+        const float* px = p.xyz + (long long)off * 3;
         const float* pc = p.new_xyz + g * 3;
-        d3[0] = fsub(px[0], pc[0]), d3[1] = fsub(px[1], pc[1]), d3[2] = fsub(px[2], pc[2]);
+        d[0] = fsub(px[0], pc[0]), d[1] = fsub(px[1], pc[1]), d[2] = fsub(px[2], pc[2]);
       }
       src_row[r] = off;
-    }
-    {  // per-channel constants -> shared memory (broadcast LDS in the epilogues instead of dependent LDGs)
-      float* cst = reinterpret_cast<float*>(bp + Cfg::OFF_CONST);
-      for (int i = threadIdx.x; i < C1 * 4; i += Cfg::ROWS) cst[i] = p.wxyz[i];
-      for (int i = threadIdx.x; i < C1; i += Cfg::ROWS) cst[C1 * 4 + i] = p.b0[i];
-      for (int i = threadIdx.x; i < C2; i += Cfg::ROWS) cst[C1 * 5 + i] = p.b1[i];
-      for (int i = threadIdx.x; i < C3; i += Cfg::ROWS) cst[C1 * 5 + C2 + i] = p.b2[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        hi[i] = __bfloat162float(__float2bfloat16_rn(d[i]));
+        lo[i] = d[i] - hi[i];
+      }
+      // k = [x_hi y_hi z_hi | x_lo y_lo z_lo | x_hi y_hi z_hi | 0 ...] against the weight row built above
+      uint8_t* xb = bp + Cfg::OFF_XYZ + (r >> 7) * 4096;
+      *reinterpret_cast<uint4*>(xb + xyzoff(r & 127, 0)) =
+          make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], lo[0]), pack_bf16(lo[1], lo[2]), pack_bf16(hi[0], hi[1]));
+      *reinterpret_cast<uint4*>(xb + xyzoff(r & 127, 1)) = make_uint4(pack_bf16(hi[2], 0.f), 0u, 0u, 0u);
     }
     if (D > 0) {
       SA_BAR();
       constexpr int CPR = D / 8;                 // 16-byte chunks per row
       constexpr int TOTAL = Cfg::ROWS * CPR;
-      constexpr int UNR = 8;
-      static_assert(TOTAL % (Cfg::ROWS * UNR) == 0, "gather unroll");
-      for (int i0 = threadIdx.x; i0 < TOTAL; i0 += Cfg::ROWS * UNR) {
-        uint4 v[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int ch = i0 + u * Cfg::ROWS;
-          const int r = ch / CPR, c8 = ch % CPR;
-          const long long off = src_row[r];
-          v[u] = off >= 0 ? reinterpret_cast<const uint4*>(p.feats + off * D)[c8] : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int ch = i0 + u * Cfg::ROWS;
-          const int r = ch / CPR, c8 = ch % CPR;
-          *reinterpret_cast<uint4*>(bp + Cfg::OFF_X + (r >> 7) * Cfg::X_BYTES + xoff(r & 127, c8 * 8)) = v[u];
-        }
+#pragma unroll 1
+      for (int ch = threadIdx.x; ch < TOTAL; ch += Cfg::ROWS) {
+        const int r = ch / CPR, c8 = ch % CPR;
+        const int off = src_row[r];
+        const uint32_t dst = base + Cfg::OFF_X + (r >> 7) * Cfg::X_BYTES + xoff(r & 127, c8 * 8);
+        const void* src = off >= 0 ? (const void*)(p.feats + (long long)off * D + c8 * 8) : (const void*)p.feats;
+        const int nbytes = off >= 0 ? 16 : 0;  // padding rows: zero fill
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   SA_BAR();
-  SA_TRACE(1);
-
-  int w_it = 0;  // consumer position in the weight ring (thread 32 only)
-  uint32_t acc_phase = 0;
-  const int row = wq * 32 + lane;                                     // row inside this thread's sub-tile
-  uint8_t* xsub = bp + Cfg::OFF_X + sub * Cfg::X_BYTES;                // this sub-tile's operand buffer
-  const float* cst = reinterpret_cast<const float*>(bp + Cfg::OFF_CONST);
+  if (tr0) SA_TRACE(1);
 
   // ---------------- layers 0 and 1: rows on M ----------------
 #pragma unroll
@@ -270,14 +334,13 @@ __global__ void __launch_bounds__(128 * SUB + 32)
     const int PANELS = layer == 0 ? Cfg::P0 : Cfg::P1;
     const int NB = layer == 0 ? Cfg::NB1 : Cfg::NB2;
     const int COUT = layer == 0 ? C1 : C2;
-    const float* bias = cst + (layer == 0 ? C1 * 4 : C1 * 5);
-    const bool has_mma = !(layer == 0 && D == 0);
-    if (has_mma && threadIdx.x == 32) {
+    const float* bias = cst + (layer == 0 ? 0 : C1);
+    if (threadIdx.x == 32) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int nb = 0; nb < NB; ++nb) {
         for (int kp = 0; kp < PANELS; ++kp) {
           const int s = w_it % STAGES;
-          mbar_wait(bar_full + 8 * s, (w_it / STAGES) & 1);
+          if (!RESIDENT || tr0) mbar_wait(bar_full + 8 * s, ((w_it / STAGES) & 1) ^ ring_par);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t db = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE);
 #pragma unroll
@@ -285,38 +348,30 @@ __global__ void __launch_bounds__(128 * SUB + 32)
             const uint64_t da = desc_kmajor(base + Cfg::OFF_X + t * Cfg::X_BYTES + kp * SF_TILE);
             for (int k = 0; k < 4; ++k) umma_bf16(tmem + t * Cfg::CW + nb * 128, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
           }
-          umma_commit(bar_empty + 8 * s);
+          if (!RESIDENT) umma_commit(bar_empty + 8 * s);
           ++w_it;
+        }
+        if (layer == 0) {  // the (dx,dy,dz) columns: one K=16 step on the un-swizzled hi/lo operands
+          const uint64_t db = desc_kmajor_nosw(base + Cfg::OFF_WXYZ + nb * 4096);
+#pragma unroll
+          for (int t = 0; t < SUB; ++t)
+            umma_bf16(tmem + t * Cfg::CW + nb * 128, desc_kmajor_nosw(base + Cfg::OFF_XYZ + t * 4096), db, SF_IDESC, PANELS != 0);
         }
       }
       umma_commit(bar_acc);
     }
     __syncwarp();
-    if (has_mma) {
-      mbar_wait(bar_acc, acc_phase);
-      acc_phase ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    SA_TRACE(2 + 2 * layer);
+    mbar_wait(bar_acc, acc_phase ^ acc_par);
+    acc_phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tr0) SA_TRACE(2 + 2 * layer);
     // epilogue: thread = row; (+ xyz terms) + bias + ReLU -> bf16 -> next operand tile (in place)
     const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16) + sub * Cfg::CW;
 #pragma unroll 1
     for (int c = 0; c < COUT / 32; ++c) {
       uint32_t v[32];
-      if (has_mma) {
-        tmem_ld32(lane_addr + c * 32, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      if (layer == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 w = *reinterpret_cast<const float4*>(cst + (c * 32 + j) * 4);
-          v[j] = __float_as_uint(fmaf(w.z, d3[2], fmaf(w.y, d3[1], fmaf(w.x, d3[0], __uint_as_float(v[j])))));
-        }
-      }
+      tmem_ld32(lane_addr + c * 32, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
@@ -332,12 +387,12 @@ __global__ void __launch_bounds__(128 * SUB + 32)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     SA_BAR();
-    SA_TRACE(3 + 2 * layer);
+    if (tr0) SA_TRACE(3 + 2 * layer);
   }
 
   // ---------------- layer 2: channels on M (one 128-channel block at a time), rows on N ----------------
   {
-    const float* b2s = cst + C1 * 5 + C2;
+    const float* b2s = cst + C1 + C2;
     const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16) + sub * 128;
 #pragma unroll 1
     for (int mb = 0; mb < Cfg::MB3; ++mb) {
@@ -345,7 +400,7 @@ __global__ void __launch_bounds__(128 * SUB + 32)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kp = 0; kp < Cfg::P2; ++kp) {
           const int s = w_it % STAGES;
-          mbar_wait(bar_full + 8 * s, (w_it / STAGES) & 1);
+          if (!RESIDENT || tr0) mbar_wait(bar_full + 8 * s, ((w_it / STAGES) & 1) ^ ring_par);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = desc_kmajor(base + Cfg::OFF_W + s * SF_TILE);
 #pragma unroll
@@ -353,16 +408,16 @@ __global__ void __launch_bounds__(128 * SUB + 32)
             const uint64_t db = desc_kmajor(base + Cfg::OFF_X + t * Cfg::X_BYTES + kp * SF_TILE);
             for (int k = 0; k < 4; ++k) umma_bf16(tmem + t * 128, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
           }
-          umma_commit(bar_empty + 8 * s);
+          if (!RESIDENT) umma_commit(bar_empty + 8 * s);
           ++w_it;
         }
         umma_commit(bar_acc);
       }
       __syncwarp();
-      mbar_wait(bar_acc, acc_phase);
+      mbar_wait(bar_acc, acc_phase ^ acc_par);
       acc_phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (mb < 4) SA_TRACE(6 + 2 * mb);
+      if (tr0 && mb < 4) SA_TRACE(6 + 2 * mb);
       const int ch = mb * 128 + wq * 32 + lane;
       const float bias = b2s[ch];
 #pragma unroll 1
@@ -382,9 +437,12 @@ __global__ void __launch_bounds__(128 * SUB + 32)
       // the next channel block reuses the same TMEM columns: every compute warp must have drained them
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       SA_BAR();
-      if (mb < 4) SA_TRACE(7 + 2 * mb);
+      if (tr0 && mb < 4) SA_TRACE(7 + 2 * mb);
     }
   }
+  if (!RESIDENT) ring_par ^= (RING_ROUNDS & 1);
+  acc_par ^= (ACC_USES & 1);
+  }  // tile loop
   SA_TRACE(14);
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS));
 #undef SA_BAR
@@ -430,7 +488,30 @@ int launch_sa(const SaParams& p, const void* w0, const void* w1, const void* w2,
   auto kern = sa_fused_kernel<NS, D, C1, C2, C3, STAGES, SUB>;
   PFPP_ENSURE_SMEM(kern, Cfg::SMEM);
   const long long tiles = (p.groups + Cfg::G - 1) / Cfg::G;
-  kern<<<(unsigned)tiles, Cfg::THREADS, Cfg::SMEM, stream>>>(m0, m1, m2, p);
+  // persistent CTAs: as many as fit on the GPU at once (shared memory and TMEM bound), each walks tiles
+  // blockIdx.x, blockIdx.x + gridDim.x, ... so barrier / TMEM / constant set-up is paid once per CTA
+  static int per_sm = 0, n_sm = 0;
+  if (!per_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    const int by_regs = 65536 / (fa.numRegs * ((Cfg::THREADS + 31) / 32 * 32));
+    per_sm = Cfg::MINB < by_regs ? Cfg::MINB : by_regs;
+    per_sm = per_sm < 1 ? 1 : per_sm;
+  }
+  // two CTAs per resident slot: the second half starts as the first retires, which keeps co-resident CTAs out of
+  // phase with each other (measured: better than exactly one persistent CTA per slot)
+  long long grid = (long long)2 * per_sm * n_sm;
+  if (grid > tiles) grid = tiles;
+  static const int grid_mode = []() {
+    const char* e = getenv("PFPP_SA_GRID");  // tuning aid: 0 = one CTA per tile, n > 0 = n CTAs per SM
+    return e ? atoi(e) : -1;
+  }();
+  if (grid_mode == 0) grid = tiles;
+  if (grid_mode > 0) grid = tiles < (long long)grid_mode * n_sm ? tiles : (long long)grid_mode * n_sm;
+  kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, stream>>>(m0, m1, m2, p);
   PFPP_RETURN_LAST();
 }
 
@@ -444,28 +525,14 @@ static int sa_dispatch(int level, const float* xyz, const float* new_xyz, const 
   if (K == 0) return PFPP_OK;
   SaParams p{xyz, new_xyz, (const __nv_bfloat16*)feats, gidx, w0_xyz, b0, b1, b2, (__nv_bfloat16*)out, N, S,
              (long long)K * S, trace};
-  // PFPP_SA_VARIANT (tuning aid, tools/bench_sa.py): depth of the weight ring per level
-  static const int variant = []() {
-    const char* e = getenv("PFPP_SA_VARIANT");
-    return e ? atoi(e) : 0;
-  }();
   switch (level) {
     case 1:
-      if (variant == 1) return launch_sa<32, 0, 64, 64, 128, 4, 1>(p, w0_feat, w1, w2, stream);
       return launch_sa<32, 0, 64, 64, 128, 2, 1>(p, w0_feat, w1, w2, stream);
     case 2:
       PFPP_CHECK_ARG(feats && w0_feat);
-      if (variant == 1) return launch_sa<64, 128, 128, 128, 256, 4, 2>(p, w0_feat, w1, w2, stream);
-      if (variant == 2) return launch_sa<64, 128, 128, 128, 256, 6, 2>(p, w0_feat, w1, w2, stream);
-      if (variant == 3) return launch_sa<64, 128, 128, 128, 256, 2, 1>(p, w0_feat, w1, w2, stream);
-      if (variant == 4) return launch_sa<64, 128, 128, 128, 256, 3, 1>(p, w0_feat, w1, w2, stream);
       return launch_sa<64, 128, 128, 128, 256, 2, 2>(p, w0_feat, w1, w2, stream);
     case 3:
       PFPP_CHECK_ARG(feats && w0_feat);
-      if (variant == 1) return launch_sa<64, 256, 256, 256, 512, 4, 2>(p, w0_feat, w1, w2, stream);
-      if (variant == 2) return launch_sa<64, 256, 256, 256, 512, 5, 2>(p, w0_feat, w1, w2, stream);
-      if (variant == 3) return launch_sa<64, 256, 256, 256, 512, 2, 1>(p, w0_feat, w1, w2, stream);
-      if (variant == 4) return launch_sa<64, 256, 256, 256, 512, 3, 1>(p, w0_feat, w1, w2, stream);
       return launch_sa<64, 256, 256, 256, 512, 2, 2>(p, w0_feat, w1, w2, stream);
     default:
       return PFPP_EINVAL;

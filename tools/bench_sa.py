@@ -50,12 +50,13 @@ for level, N, S, NS, D, C1, C2, C3 in LEVELS:
     if "--trace" in sys.argv:
         rows_per_cta = 128 if level == 1 else 256
         grid = (K * S * NS + rows_per_cta - 1) // rows_per_cta
-        tr = torch.zeros(grid, 16, dtype=torch.int64, device=dev)
+        tr = torch.zeros(grid, 16, dtype=torch.int64, device=dev)  # persistent CTAs stamp their first tile only
         _lib.call("pfpp_sa_fused_trace", level, xyz.data_ptr(), new_xyz.data_ptr(), feats.data_ptr() if D else None,
                   gidx.data_ptr(), K, N, S, w0.data_ptr() if D else None, wxyz.data_ptr(), b0.data_ptr(), w1.data_ptr(),
                   b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out.data_ptr(), tr.data_ptr())
         torch.cuda.synchronize()
         t = tr.cpu().numpy()
+        t = t[t[:, 14] > 0]  # CTAs that ran
         rel = t - t[:, :1]
         names = ["start", "gather done", "L0 mma done", "L0 epi done", "L1 mma done", "L1 epi done", "L2 mb0 mma", "L2 mb0 epi",
                  "L2 mb1 mma", "L2 mb1 epi", "L2 mb2 mma", "L2 mb2 epi", "L2 mb3 mma", "L2 mb3 epi", "end"]
