@@ -132,47 +132,57 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Small-M variant: 64x64x16 CTA tile, 256 threads, 4x4 register micro-tile.  Used when the 128x128 grid would
-// leave most of the 148 SMs idle (the denoiser's output heads: M = number of fragments).  Every output element
-// is still one sequential fmaf chain over k = 0..K-1, so both variants produce bit-identical results.
-#define SBM 64
-#define SBN 64
+// Small-M variant: 32x32x16 CTA tile, 64 threads, 4x4 register micro-tile.  Used when the 128x128 grid would
+// leave most of the 148 SMs idle (the denoiser's output heads: M = number of fragments).  With so few rows the
+// GEMM is bound by the latency of its serial K loop, not by FLOPs; small tiles put 4-10 CTAs on every SM so that
+// the loops of different CTAs hide each other's global-load latency.  Every output element is still one
+// sequential fmaf chain over k = 0..K-1, so both variants produce bit-identical results.
+#define SBM 32
+#define SBN 32
+#define SBK 64  // deep k-tiles: 16 independent 16-byte loads per thread in flight, 4x fewer serial iterations
 template <int EPI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
     gemm_f32_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                           const float* __restrict__ bias, const float* residual, int ldr, float* C, int ldc, int M,
                           int N, int K) {
-  __shared__ __align__(16) float As[2][GBK][SBM + GPAD];
-  __shared__ __align__(16) float Ws[2][GBK][SBN + GPAD];
+  __shared__ __align__(16) float As[2][SBK][SBM + GPAD];
+  __shared__ __align__(16) float Ws[2][SBK][SBN + GPAD];
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
+  const int tx = tid & 7, ty = tid >> 3;
   const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
-  const int lrow = tid >> 2;     // 0..63
-  const int lk = (tid & 3) * 4;  // 0,4,8,12
-  float4 ra, rw;
+  const int lrow = tid >> 4;     // 0..3 (+4 h)
+  const int lk = (tid & 15) * 4;  // 0,4,..,60: a quarter-warp reads 256 contiguous bytes of one row
+  float4 ra[8], rw[8];
   auto load_tiles = [&](int k0) {
-    const int gm = m0 + lrow, gn = n0 + lrow, gk = k0 + lk;
-    ra = (gm < M && gk < K) ? *reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk) : make_float4(0.f, 0.f, 0.f, 0.f);
-    rw = (gn < N && gk < K) ? *reinterpret_cast<const float4*>(W + (size_t)gn * ldw + gk) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int gm = m0 + lrow + 4 * h, gn = n0 + lrow + 4 * h, gk = k0 + lk;
+      ra[h] = (gm < M && gk < K) ? *reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rw[h] = (gn < N && gk < K) ? *reinterpret_cast<const float4*>(W + (size_t)gn * ldw + gk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   };
   auto store_tiles = [&](int buf) {
-    As[buf][lk + 0][lrow] = ra.x, As[buf][lk + 1][lrow] = ra.y, As[buf][lk + 2][lrow] = ra.z, As[buf][lk + 3][lrow] = ra.w;
-    Ws[buf][lk + 0][lrow] = rw.x, Ws[buf][lk + 1][lrow] = rw.y, Ws[buf][lk + 2][lrow] = rw.z, Ws[buf][lk + 3][lrow] = rw.w;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      const int r = lrow + 4 * h;
+      As[buf][lk + 0][r] = ra[h].x, As[buf][lk + 1][r] = ra[h].y, As[buf][lk + 2][r] = ra[h].z, As[buf][lk + 3][r] = ra[h].w;
+      Ws[buf][lk + 0][r] = rw[h].x, Ws[buf][lk + 1][r] = rw[h].y, Ws[buf][lk + 2][r] = rw[h].z, Ws[buf][lk + 3][r] = rw[h].w;
+    }
   };
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const int nk = (K + GBK - 1) / GBK;
+  const int nk = (K + SBK - 1) / SBK;
   load_tiles(0);
   store_tiles(0);
   __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < nk) load_tiles((kt + 1) * GBK);
-#pragma unroll
-    for (int k = 0; k < GBK; ++k) {
+    if (kt + 1 < nk) load_tiles((kt + 1) * SBK);
+#pragma unroll 16
+    for (int k = 0; k < SBK; ++k) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
       const float4 b4 = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
       const float a[4] = {a4.x, a4.y, a4.z, a4.w};
@@ -226,11 +236,11 @@ extern "C" int pfpp_gemm_f32(const float* A, int lda, const float* W, int ldw, c
   if (M == 0) return PFPP_OK;
   dim3 grid(pfpp_cdiv(N, GBN), pfpp_cdiv(M, GBM));
   dim3 sgrid(pfpp_cdiv(N, SBN), pfpp_cdiv(M, SBM));
-  const bool small = grid.x * grid.y < 148;  // the big tiles would not even give every SM one CTA
+  const bool small = grid.x * grid.y < 74;  // the big tiles would leave more than half of the SMs idle
 #define PFPP_GEMM_CASE(E)                                                                                      \
   case E:                                                                                                      \
     if (small)                                                                                                 \
-      gemm_f32_small_kernel<E><<<sgrid, 256, 0, stream>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K); \
+      gemm_f32_small_kernel<E><<<sgrid, 64, 0, stream>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K);  \
     else                                                                                                       \
       gemm_f32_kernel<E><<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K);      \
     break;

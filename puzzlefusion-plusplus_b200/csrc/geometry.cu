@@ -406,11 +406,14 @@ extern "C" int pfpp_group_max(const void* in, long long G, int ns, int C, int ld
 
 // ---------------------------------------------------------------------------------------------
 // vector quantisation (quantizer.py:42-63): per 16-d chunk, argmin_c (|z|^2 + |e_c|^2) - 2 z.e_c
-// (first minimum), output z + (e - z).  Codebook (64 KB) + |e|^2 staged in shared memory; one
-// thread per chunk, all threads of a warp read the same code row (smem broadcast).
+// (first minimum), output z + (e - z).  Codebook (64 KB) + |e|^2 staged in shared memory; all threads of a
+// warp read the same code row (smem broadcast).  A broadcast LDS.128 returns 512 B per warp, so the scan is
+// bound by shared-memory return bandwidth unless every code row is reused: each thread scans for VQ_R chunks
+// at once (the arithmetic per (chunk, code) pair is unchanged).
 // ---------------------------------------------------------------------------------------------
 #define VQ_DIM 16
-#define VQ_THREADS 128
+#define VQ_THREADS 64
+#define VQ_R 4
 
 template <typename InT>
 __global__ void __launch_bounds__(VQ_THREADS)
@@ -419,7 +422,8 @@ __global__ void __launch_bounds__(VQ_THREADS)
   extern __shared__ float sm[];
   float* cb = sm;                      // [n_codes][16]
   float* cn = sm + (size_t)n_codes * VQ_DIM;  // [n_codes]
-  for (int i = threadIdx.x; i < n_codes * VQ_DIM; i += VQ_THREADS) cb[i] = codebook[i];
+  for (int i = threadIdx.x; i < n_codes * VQ_DIM / 4; i += VQ_THREADS)
+    reinterpret_cast<float4*>(cb)[i] = reinterpret_cast<const float4*>(codebook)[i];
   __syncthreads();
   for (int c = threadIdx.x; c < n_codes; c += VQ_THREADS) {
     float s = 0.f;
@@ -427,31 +431,44 @@ __global__ void __launch_bounds__(VQ_THREADS)
     cn[c] = s;
   }
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * VQ_THREADS + threadIdx.x; i < n_chunks;
-       i += (long long)gridDim.x * VQ_THREADS) {
-    float zv[VQ_DIM];
-    float zz = 0.f;
+  const long long T = (long long)gridDim.x * VQ_THREADS;
+  for (long long i0 = (long long)blockIdx.x * VQ_THREADS + threadIdx.x; i0 < n_chunks; i0 += T * VQ_R) {
+    float zv[VQ_R][VQ_DIM], zz[VQ_R], best[VQ_R];
+    int bi[VQ_R];
 #pragma unroll
-    for (int d = 0; d < VQ_DIM; ++d) {
-      zv[d] = (float)z[i * VQ_DIM + d];
-      zz += zv[d] * zv[d];
+    for (int r = 0; r < VQ_R; ++r) {
+      const long long i = i0 + r * T;
+      zz[r] = 0.f, best[r] = INFINITY, bi[r] = 0;
+#pragma unroll
+      for (int d = 0; d < VQ_DIM; ++d) {
+        zv[r][d] = i < n_chunks ? (float)z[i * VQ_DIM + d] : 0.f;
+        zz[r] += zv[r][d] * zv[r][d];
+      }
     }
-    float best = INFINITY;
-    int bi = 0;
     for (int c = 0; c < n_codes; ++c) {
       const float4* e = reinterpret_cast<const float4*>(cb + c * VQ_DIM);
-      float dot = 0.f;
+      const float4 e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
+      const float en = cn[c];
 #pragma unroll
-      for (int d4 = 0; d4 < VQ_DIM / 4; ++d4) {
-        float4 v = e[d4];
-        dot += zv[4 * d4] * v.x + zv[4 * d4 + 1] * v.y + zv[4 * d4 + 2] * v.z + zv[4 * d4 + 3] * v.w;
+      for (int r = 0; r < VQ_R; ++r) {
+        float dot = 0.f;
+        dot += zv[r][0] * e0.x + zv[r][1] * e0.y + zv[r][2] * e0.z + zv[r][3] * e0.w;
+        dot += zv[r][4] * e1.x + zv[r][5] * e1.y + zv[r][6] * e1.z + zv[r][7] * e1.w;
+        dot += zv[r][8] * e2.x + zv[r][9] * e2.y + zv[r][10] * e2.z + zv[r][11] * e2.w;
+        dot += zv[r][12] * e3.x + zv[r][13] * e3.y + zv[r][14] * e3.z + zv[r][15] * e3.w;
+        const float dist = (zz[r] + en) - 2.0f * dot;
+        if (dist < best[r]) best[r] = dist, bi[r] = c;
       }
-      float dist = (zz + cn[c]) - 2.0f * dot;
-      if (dist < best) best = dist, bi = c;
     }
-    if (codes) codes[i] = bi;
 #pragma unroll
-    for (int d = 0; d < VQ_DIM; ++d) out[i * VQ_DIM + d] = fadd(zv[d], fsub(cb[bi * VQ_DIM + d], zv[d]));
+    for (int r = 0; r < VQ_R; ++r) {
+      const long long i = i0 + r * T;
+      if (i < n_chunks) {
+        if (codes) codes[i] = bi[r];
+#pragma unroll
+        for (int d = 0; d < VQ_DIM; ++d) out[i * VQ_DIM + d] = fadd(zv[r][d], fsub(cb[bi[r] * VQ_DIM + d], zv[r][d]));
+      }
+    }
   }
 }
 
@@ -461,7 +478,7 @@ extern "C" int pfpp_vq(const void* z, int z_is_bf16, long long n_chunks, const f
   if (n_chunks == 0) return PFPP_OK;
   size_t smem = (size_t)n_codes * (VQ_DIM + 1) * sizeof(float);
   if (smem > 200 * 1024) return PFPP_EUNSUPPORTED;
-  int grid = (int)((n_chunks + VQ_THREADS - 1) / VQ_THREADS);
+  int grid = (int)((n_chunks + VQ_THREADS * VQ_R - 1) / (VQ_THREADS * VQ_R));
   if (grid > 148 * 3) grid = 148 * 3;
   if (z_is_bf16) {
     PFPP_ENSURE_SMEM(vq_kernel<__nv_bfloat16>, smem);

@@ -235,11 +235,11 @@ class Engine:
             self.gemm(ff, 4 * C, lw["ff2"], h, C, M, EPI_NONE, residual=h, ldr=C)
             if trace is not None:
                 trace[f"layer{li}"] = h.clone()
+        eps = self.buf("eps", (F, 8), torch.float32)
         pooled = self.buf("pooled", (F, C), torch.float32)
         h0 = self.buf("head0", (F, 2 * C), torch.float32)
         ht = self.buf("head_t", (F, C // 2), torch.float32)
         hr = self.buf("head_r", (F, C // 2), torch.float32)
-        eps = self.buf("eps", (F, 8), torch.float32)
         call("pfpp_mean_pool", h.data_ptr(), F, L, C, 0, pooled.data_ptr())
         self.gemm(pooled, C, w.head0, h0, 2 * C, F, EPI_SILU, force_f32=True)
         self.gemm(h0, 2 * C, w.head_t2, ht, C // 2, F, EPI_SILU, force_f32=True)

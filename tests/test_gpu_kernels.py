@@ -406,3 +406,4 @@ def test_attention_tcgen05_block_diagonal(lib, F, tiles):
     q, k, v = [t.reshape(F, L, H, D).transpose(1, 2) for t in qkv.float().chunk(3, -1)]
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(F, L, C)
     assert (o - ref).abs().max() <= 2e-2, (o - ref).abs().max()
+
