@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--chunk", type=int, default=32)
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     ap.add_argument("--no-graph", action="store_true", help="launch every DDPM step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=1,
                     help="the batch is split over this many CUDA streams (interleaved by one host thread) so that the "
                          "latency-bound geometry kernels of one half overlap the tensor-core kernels of the other")
     return ap.parse_args()

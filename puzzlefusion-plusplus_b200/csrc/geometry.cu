@@ -5,6 +5,8 @@
 // xyz tiles are staged once in shared memory (SoA), distances live in registers, reductions are
 // warp shuffles.  All floating-point decisions replicate the oracle's op order with individually
 // rounded fp32 ops so that indices are bit-identical (see oracle/third_party.py, oracle/encoder.py).
+#include <climits>
+
 #include "common.cuh"
 #include "../../include/pfpp.h"
 
@@ -87,21 +89,30 @@ extern "C" int pfpp_pose_apply(const float* pts, const int* seg_start, const int
 #define FPS_THREADS 256
 
 // Block-wide arg-max of (distance, then lower owner thread, then lower point index) with two warp-level
-// redux.sync passes instead of shuffle trees.  Distances are >= 0, so their bit patterns order like
-// unsigned integers; `ud` = bits + 1, with 0 reserved for "this thread owns no point".  Within a thread the
-// caller keeps the first (lowest-index) maximum; between lanes / warps the lowest one wins, which is the
-// (lower thread, lower index) tie-break of torch_cluster's strided scan + tree reduce.
-// red_d / red_k: [2][FPS_THREADS/32] double-buffered partials -> one barrier per round.
-__device__ __forceinline__ int fps_block_argmax(unsigned ud, int n, int par, unsigned (*red_d)[FPS_THREADS / 32],
-                                                int (*red_k)[FPS_THREADS / 32], int lane, int warp) {
-  const unsigned m = __reduce_max_sync(0xffffffffu, ud);
+// redux.sync passes instead of shuffle trees.  Distances are >= 0, so their bit patterns order like signed
+// integers; points that do not exist carry the distance -1.0f (a negative integer) and can never win.  Within
+// a thread the caller keeps the first (lowest-index) maximum; between lanes / warps the lowest one wins, which
+// is the (lower thread, lower index) tie-break of torch_cluster's strided scan + tree reduce.
+// The partials are double-buffered by round parity -> one barrier per round.
+// `red` points at this CTA's [2][2][FPS_THREADS/32] int partials (parity, {distance, index}, warp) as a 32-bit
+// shared-window address, so the loads/stores are plain LDS/STS with immediate offsets.
+__device__ __forceinline__ int fps_block_argmax(int ud, int n, int par, uint32_t red, int lane, int warp) {
+  constexpr int W = FPS_THREADS / 32;
+  const int m = __reduce_max_sync(0xffffffffu, ud);
   const unsigned win = __ballot_sync(0xffffffffu, ud == m);
-  if (lane == __ffs(win) - 1) red_d[par][warp] = m, red_k[par][warp] = n;
+  const uint32_t slot = red + (uint32_t)par * (2 * W * 4);
+  if (lane == __ffs(win) - 1) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(slot + warp * 4), "r"(m) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(slot + (W + warp) * 4), "r"(n) : "memory");
+  }
   __syncthreads();
-  const unsigned pd = lane < FPS_THREADS / 32 ? red_d[par][lane] : 0u;
-  const int pk = lane < FPS_THREADS / 32 ? red_k[par][lane] : 0;
-  const unsigned m2 = __reduce_max_sync(0xffffffffu, pd);
-  const unsigned win2 = __ballot_sync(0xffffffffu, pd == m2 && lane < FPS_THREADS / 32);
+  int pd = INT_MIN, pk = 0;
+  if (lane < W) {
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pd) : "r"(slot + lane * 4) : "memory");
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pk) : "r"(slot + (W + lane) * 4) : "memory");
+  }
+  const int m2 = __reduce_max_sync(0xffffffffu, pd);
+  const unsigned win2 = __ballot_sync(0xffffffffu, pd == m2);
   return __shfl_sync(0xffffffffu, pk, __ffs(win2) - 1);
 }
 
@@ -114,8 +125,9 @@ __global__ void __launch_bounds__(FPS_THREADS)
   float* sx = sm;
   float* sy = sm + N;
   float* sz = sm + 2 * N;
-  __shared__ unsigned red_d[2][FPS_THREADS / 32];
-  __shared__ int red_k[2][FPS_THREADS / 32];
+  int* hist = reinterpret_cast<int*>(sm + 3 * N);  // [S] selected indices, written out after the loop
+  __shared__ int red_buf[2 * 2 * (FPS_THREADS / 32)];
+  const uint32_t red = (uint32_t)__cvta_generic_to_shared(red_buf);
 
   const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = src_slot ? src_slot[k] : k;
@@ -145,34 +157,37 @@ __global__ void __launch_bounds__(FPS_THREADS)
     px[i] = ok ? sx[n] : 0.f;
     py[i] = ok ? sy[n] : 0.f;
     pz[i] = ok ? sz[n] : 0.f;
-    dist[i] = 5e4f;
+    dist[i] = ok ? 5e4f : -1.0f;  // a slot without a point keeps -1 (min(-1, d) = -1) and never wins the arg-max
   }
   int cur = start ? start[k] : 0;
-  int* oi = out_idx + (size_t)k * S;
-  float* ox = out_xyz ? out_xyz + (size_t)k * S * 3 : nullptr;
 
-  for (int m = 0; m < S; ++m) {
-    float cx = sx[cur], cy = sy[cur], cz = sz[cur];
-    if (tid == 0) {
-      oi[m] = cur;
-      if (ox) ox[3 * m] = cx, ox[3 * m + 1] = cy, ox[3 * m + 2] = cz;
-    }
-    if (m + 1 == S) break;
-    unsigned bd = 0u;  // best of this thread's points: distance bits + 1 (0 = none), first maximum wins
-    int bn = 0;
+  // The loop body is issue-bound (every resident warp runs it S times), so it is branch-free: no per-point
+  // validity test, selects instead of branches for the per-thread best, and the outputs are written after the loop.
+  for (int m = 0; m + 1 < S; ++m) {
+    const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+    if (tid == 0) hist[m] = cur;
+    int bd = 0, bi = 0;
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
-      int n = tid + i * FPS_THREADS;
-      if (n < N) {
-        float dx = fsub(cx, px[i]), dy = fsub(cy, py[i]), dz = fsub(cz, pz[i]);
-        float dd = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-        dd = fminf(dist[i], dd);
-        dist[i] = dd;
-        const unsigned u = __float_as_uint(dd) + 1u;
-        if (u > bd) bd = u, bn = n;
-      }
+      const float dx = fsub(cx, px[i]), dy = fsub(cy, py[i]), dz = fsub(cz, pz[i]);
+      float dd = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+      dd = fminf(dist[i], dd);
+      dist[i] = dd;
+      const int u = __float_as_int(dd);
+      const bool better = (i == 0) || (u > bd);  // strict: the first (lowest-index) maximum of the thread wins
+      bd = better ? u : bd;
+      bi = better ? i : bi;
     }
-    cur = fps_block_argmax(bd, bn, m & 1, red_d, red_k, lane, warp);
+    cur = fps_block_argmax(bd, tid + bi * FPS_THREADS, m & 1, red, lane, warp);
+  }
+  if (tid == 0) hist[S - 1] = cur;
+  __syncthreads();
+  int* oi = out_idx + (size_t)k * S;
+  float* ox = out_xyz ? out_xyz + (size_t)k * S * 3 : nullptr;
+  for (int m = tid; m < S; m += FPS_THREADS) {
+    const int c = hist[m];
+    oi[m] = c;
+    if (ox) ox[3 * m] = sx[c], ox[3 * m + 1] = sy[c], ox[3 * m + 2] = sz[c];
   }
 }
 
@@ -182,8 +197,8 @@ __global__ void __launch_bounds__(FPS_THREADS)
                      const int* __restrict__ cloud_len, const int* __restrict__ n_samples,
                      const int* __restrict__ start, float* __restrict__ dist, const int* __restrict__ out_start,
                      int* __restrict__ out_idx) {
-  __shared__ unsigned red_d[2][FPS_THREADS / 32];
-  __shared__ int red_k[2][FPS_THREADS / 32];
+  __shared__ int red_buf[2 * 2 * (FPS_THREADS / 32)];
+  const uint32_t red = (uint32_t)__cvta_generic_to_shared(red_buf);
   const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = cloud_len[k], S = n_samples[k];
   const float* p = src + 3 * (size_t)cloud_start[k];
@@ -195,24 +210,24 @@ __global__ void __launch_bounds__(FPS_THREADS)
     if (tid == 0) oi[m] = cur;
     if (m + 1 == S) break;
     float cx = p[3 * cur], cy = p[3 * cur + 1], cz = p[3 * cur + 2];
-    unsigned bd = 0u;
+    int bd = INT_MIN;  // a thread without points never wins
     int bn = 0;
     for (int n = tid; n < N; n += FPS_THREADS) {
       float dx = fsub(cx, p[3 * n]), dy = fsub(cy, p[3 * n + 1]), dz = fsub(cz, p[3 * n + 2]);
       float dd = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
       dd = fminf(d[n], dd);
       d[n] = dd;
-      const unsigned u = __float_as_uint(dd) + 1u;
+      const int u = __float_as_int(dd);
       if (u > bd) bd = u, bn = n;
     }
-    cur = fps_block_argmax(bd, bn, m & 1, red_d, red_k, lane, warp);
+    cur = fps_block_argmax(bd, bn, m & 1, red, lane, warp);
   }
 }
 
 template <bool ROTATE>
 static int launch_fps(const float* src, const int* src_slot, int K, int N, int S, const float* quat, int quat_stride,
                       const int* start, float* rot_out, int* out_idx, float* out_xyz, cudaStream_t stream) {
-  size_t smem = (size_t)3 * N * sizeof(float);
+  size_t smem = (size_t)3 * N * sizeof(float) + (size_t)S * sizeof(int);
 #define PFPP_FPS_CASE(PPT)                                                                                   \
   fps_kernel<PPT, ROTATE><<<K, FPS_THREADS, smem, stream>>>(src, src_slot, N, S, quat, quat_stride, start, \
                                                              rot_out, out_idx, out_xyz)
