@@ -365,6 +365,23 @@ def main():
     else:
         peak = 72.0  # fp32 FFMA nominal: 148 SM x 128 lanes x 2 x 1.9 GHz (no measured fp32 peak is provided)
         peak_src = "nominal fp32 FFMA"
+    def ncu_traffic(entry):
+        """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+        `ncu --set full` capture of this command (profiles/r1d_*_full_summary.txt); None if there is no capture."""
+        fname = {"pfpp_sa_fused": "r1d_sa_full_summary.txt", "pfpp_gemm_bf16": "r1d_gemm_full_summary.txt",
+                 "pfpp_attention_tc": "r1d_attention_full_summary.txt"}.get(entry)
+        try:
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot, n = 0.0, 0
+            for ln in open(os.path.join(ROOT, "profiles", fname)):
+                f = ln.split()
+                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(f[1]) * unit[f[2].strip("[]")]
+                    n += f[0] == "dram__bytes_read.sum"
+            return tot / n if n else None
+        except Exception:
+            return None
+
     tensor_kernels = {k: v for k, v in kernels.items() if v["tflops"]}
     dom = max(tensor_kernels, key=lambda k: tensor_kernels[k]["ms_per_ddpm_step"])
     for v in kernels.values():
@@ -382,7 +399,9 @@ def main():
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
-                     "frac": kernels[dom]["tflops"] / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "frac": kernels[dom]["tflops"] / peak if peak else None, "traffic": ncu_traffic(dom),
+                     "traffic_note": "DRAM bytes per launch (read + write), mean over the launches of profiles/r1d_*_full_summary.txt",
+                     "peak_source": peak_src,
                      "avg_launch_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["share_of_ddpm_step"],
                      "whole_step": {"algorithmic_tflop_per_ddpm_step": step_flops / 1e12,
                                     "achieved_tflops_timed_region": step_flops / (ddpm_ms_timed * 1e-3) / 1e12,

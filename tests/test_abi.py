@@ -55,3 +55,37 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_argument_errors_are_negative_codes_without_touching_the_gpu():
+    """Error behaviour of the ABI (include/pfpp.h conventions): NULL / out-of-range arguments return a negative code
+    before any CUDA call, empty problems (0 clouds / rows / segments) return 0 without launching -- so both can be
+    checked on a machine without a GPU."""
+    from puzzlefusion_plusplus_b200 import _lib
+    lib = _lib.load()
+    P = ctypes.c_void_p
+    one = ctypes.c_void_p(16)  # a non-NULL, 16-byte aligned dummy pointer that is never dereferenced on these paths
+    null = P(None)
+    f = ctypes.c_float
+    # NULL pointers
+    assert lib.pfpp_fps(null, 1, 8, 4, null, one, null, null) < 0
+    assert lib.pfpp_ball_query(one, null, 1, 8, 4, f(0.04), 32, one, null) < 0
+    assert lib.pfpp_gemm_bf16(null, 8, one, 8, null, null, 0, one, 8, 0, 4, 8, 8, 0, null) < 0
+    assert lib.pfpp_gemm_f32(one, 4, null, 4, null, null, 0, one, 4, 4, 4, 4, 0, null) < 0
+    # shapes the kernels do not support
+    assert lib.pfpp_fps(one, 1, 8, 9, null, one, null, null) < 0                      # more samples than points
+    assert lib.pfpp_gemm_bf16(one, 12, one, 12, null, null, 0, one, 8, 0, 4, 8, 12, 0, null) < 0  # K % 8 != 0
+    assert lib.pfpp_gemm_f32(one, 4, one, 4, null, null, 0, one, 4, 4, 4, 4, 99, null) < 0        # unknown epilogue
+    assert lib.pfpp_attention_tc(one, 1000, 1536, 512, one, one, 1, 513, 8, 0, one, 512, null) < 0   # segment > 512
+    assert lib.pfpp_attention_tc(one, 1000, 1536, 512, one, one, 1, 500, 7, 0, one, 512, null) < 0   # C != heads*64
+    assert lib.pfpp_layernorm(one, null, null, null, null, null, 0, 10, 384, 0, one, null, null) < 0  # C not 256/512
+    assert lib.pfpp_sa_fused(4, one, one, one, one, 1, 8, 4, one, one, one, one, one, one, one, one, null) < 0  # level
+    # empty problems are fine and launch nothing
+    assert lib.pfpp_fps(one, 0, 8, 4, null, one, null, null) == 0
+    assert lib.pfpp_ball_query(one, one, 0, 8, 4, f(0.04), 32, one, null) == 0
+    assert lib.pfpp_gemm_bf16(one, 8, one, 8, null, null, 0, one, 8, 0, 0, 8, 8, 0, null) == 0
+    assert lib.pfpp_gemm_f32(one, 4, one, 4, null, null, 0, one, 4, 0, 4, 4, 0, null) == 0
+    assert lib.pfpp_attention_tc(one, 0, 1536, 512, one, one, 0, 500, 8, 0, one, 512, null) == 0
+    assert lib.pfpp_layernorm(one, null, null, null, null, null, 0, 0, 512, 0, one, null, null) == 0
+    assert lib.pfpp_sa_fused(1, one, one, null, one, 0, 8, 4, null, one, one, one, one, one, one, one, null) == 0
+    assert lib.pfpp_vq(one, 0, 0, one, 1024, one, null, null) == 0
