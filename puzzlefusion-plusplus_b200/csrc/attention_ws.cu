@@ -48,7 +48,7 @@ constexpr uint32_t AW_COL_S = 0, AW_COL_O = 256;
 constexpr float AW_LAZY = 8.0f;  // log2 units
 
 // barrier slots (8 bytes each); per-group barriers are indexed [w], per-group-per-buffer ones [2 w + buf]
-enum { B_Q = 0, B_QFREE = 2, B_K = 4, B_V = 8, B_S = 12, B_SFREE = 16, B_P = 20, B_PV = 24, B_COUNT = 28 };
+enum { B_Q = 0, B_QFREE = 2, B_K = 4, B_V = 8, B_S = 12, B_SFREE = 16, B_P = 20, B_PV = 24, B_TOK = 28, B_COUNT = 30 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
   auto tile_steps = [&](int kb) { return (min(tile_stride, len - kb * tile_stride) + AW_STEP - 1) / AW_STEP; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + 8 * i, (i >= B_SFREE && i < B_PV) ? 128u : 1u);
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + 8 * i, ((i >= B_SFREE && i < B_PV) || i >= B_TOK) ? 128u : 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 10) {
@@ -365,6 +365,18 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
     const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
     const uint32_t o_addr = lane_addr + AW_COL_O + w * AW_D;
     int n = 0;  // steps consumed by this group so far
+    // Global mode: the two groups take turns on the MUFU pipe (B_TOK + w is completed by the OTHER group when it has
+    // finished an exponential phase): without the hand-over they drift into lockstep, exponentiate at the same
+    // time at half rate each and then idle in their TMEM-load / max / barrier phases at the same time as well.
+    // Group 0 runs tiles 0,2 and group 1 tiles 1,3 with the same number of steps per tile, so group 1 never has
+    // more steps than group 0.
+    const bool take_turns = (block == 0) && nt > 1;
+    int steps_other = 0;  // total steps of the other group
+    if (take_turns) {
+      int per_tile = 0;
+      for (int kb = 0; kb < nt; ++kb) per_tile += tile_steps(kb);
+      steps_other = per_tile * ((nt - (1 - w) + 1) / 2);
+    }
     const int blk_lo = block ? (row / block) * block : 0;  // first key (tile-relative) of this row's block
     for (int jq = w; jq < nt; jq += 2) {
       const int tile_len = min(tile_stride, len - jq * tile_stride);
@@ -446,8 +458,14 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
           if (n >= 2) mbar_wait(bars + 8 * (B_PV + 2 * w + b), ((n >> 1) - 1) & 1);  // P panel b drained by step n - 2
           uint8_t* prow = base_ptr + AW_OFF_P + (2 * w + b) * AW_TILE + row * 128;
           const float nm = (m_used == -INFINITY) ? 0.f : -m_used;
+          if (take_turns) {
+            // group 0 waits for group 1's phase n-1, group 1 for group 0's phase n
+            const int need = w == 0 ? n - 1 : n;
+            if (need >= 0 && need < steps_other) mbar_wait(bars + 8 * (B_TOK + w), need & 1);
+          }
           l += full ? exp_store<true>(s, scale_log2e, nm, prow, row, 0, 8)
                     : exp_store<false>(s, scale_log2e, nm, prow, row, clo, chi);
+          if (take_turns) mbar_arrive(bars + 8 * (B_TOK + (w ^ 1)));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> tensor-core reads
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(bars + 8 * (B_P + 2 * w + b));
