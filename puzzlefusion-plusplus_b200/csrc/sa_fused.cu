@@ -449,6 +449,249 @@ __global__ void __launch_bounds__(128 * SUB + 32, SaCfg<NS, D, C1, C2, C3, STAGE
 #undef SA_TRACE
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Resident-weight variant (levels whose three weight matrices fit in shared memory next to the operand tiles:
+// level 1 = 32 KB, level 2 = 128 KB).  One persistent CTA per SM holds ALL weight tiles for the whole launch
+// (one TMA burst at CTA start, no weight ring, no producer warp, no per-tile L2 traffic for weights) and runs
+// NWG independent warpgroups.  Each warpgroup walks its own sequence of 128-row tiles with its own operand
+// buffer, TMEM columns, accumulator barrier and named barrier, so the groups drift out of phase and the tensor
+// pipe works for one group while the others gather or run epilogues -- the overlap that two co-resident CTAs
+// of the streaming kernel give, without streaming the weights twice.
+// ------------------------------------------------------------------------------------------------------------
+template <int NS, int D, int C1, int C2, int C3, int NWG>
+struct SaResCfg {
+  static constexpr int THREADS = 128 * NWG;
+  static constexpr int P0 = D / 64, P1 = (C1 + 63) / 64, P2 = (C2 + 63) / 64;
+  static constexpr int NB1 = (C1 + 127) / 128, NB2 = (C2 + 127) / 128, MB3 = C3 / 128;
+  static constexpr int X_PANELS = (P0 > P1 ? (P0 > P2 ? P0 : P2) : (P1 > P2 ? P1 : P2));
+  static constexpr int W0_TILES = NB1 * P0, W1_TILES = NB2 * P1, W2_TILES = MB3 * P2;
+  static constexpr uint32_t OFF_W0 = 0;
+  static constexpr uint32_t OFF_W1 = OFF_W0 + W0_TILES * SF_TILE;
+  static constexpr uint32_t OFF_W2 = OFF_W1 + W1_TILES * SF_TILE;
+  static constexpr uint32_t OFF_X = OFF_W2 + W2_TILES * SF_TILE;        // [NWG][X_PANELS] operand panels
+  static constexpr uint32_t X_BYTES = X_PANELS * SF_TILE;
+  static constexpr uint32_t OFF_XYZ = OFF_X + NWG * X_BYTES;            // [NWG][128 x 16] bf16 hi/lo offsets
+  static constexpr int WXYZ_ROWS = NB1 * 128;
+  static constexpr uint32_t OFF_WXYZ = OFF_XYZ + NWG * 4096;
+  static constexpr uint32_t OFF_BAR = OFF_WXYZ + WXYZ_ROWS * 32;        // bar_w | bar_acc[NWG] | tmem slot
+  static constexpr uint32_t OFF_ROWS = OFF_BAR + 128;                   // [NWG][128] int32 gather offsets
+  static constexpr uint32_t OFF_CONST = OFF_ROWS + NWG * 512;           // b0 | b1 | b2 (fp32)
+  static constexpr uint32_t SMEM = OFF_CONST + (C1 + C2 + C3) * 4 + 1024;
+  static constexpr int TMEM_COLS = NWG * 128 > 256 ? 512 : (NWG * 128 > 128 ? 256 : 128);
+  static constexpr int GS = 128 / NS;                                   // groups per tile
+  static_assert(NB1 == 1 && NB2 == 1, "layers 0/1 must fit one 128-column accumulator block");
+  static_assert(SMEM <= 227 * 1024, "resident weights + operand tiles exceed shared memory");
+};
+
+template <int NS, int D, int C1, int C2, int C3, int NWG>
+__global__ void __launch_bounds__(128 * NWG, 1)
+    sa_resident_kernel(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
+                       const __grid_constant__ CUtensorMap map_w2, const SaParams p) {
+  using Cfg = SaResCfg<NS, D, C1, C2, C3, NWG>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_w = base + Cfg::OFF_BAR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = warp >> 2, wq = warp & 3;       // warpgroup and TMEM lane quarter
+  const int t128 = threadIdx.x & 127;             // thread inside its warpgroup
+  const uint32_t bar_acc = bar_w + 8 + 8 * wg;
+  const uint32_t tmem_slot = bar_w + 8 + 8 * NWG;
+  const long long n_tiles = (p.groups + Cfg::GS - 1) / Cfg::GS;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int g = 0; g < NWG; ++g) mbar_init(bar_w + 8 + 8 * g, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // every weight tile of the level, once
+    mbar_expect_tx(bar_w, (Cfg::W0_TILES + Cfg::W1_TILES + Cfg::W2_TILES) * SF_TILE);
+    if (D > 0)
+      for (int kp = 0; kp < Cfg::P0; ++kp) tma_load_2d(base + Cfg::OFF_W0 + kp * SF_TILE, &map_w0, bar_w, kp * 64, 0);
+    for (int kp = 0; kp < Cfg::P1; ++kp) tma_load_2d(base + Cfg::OFF_W1 + kp * SF_TILE, &map_w1, bar_w, kp * 64, 0);
+    for (int mb = 0; mb < Cfg::MB3; ++mb)
+      for (int kp = 0; kp < Cfg::P2; ++kp)
+        tma_load_2d(base + Cfg::OFF_W2 + (mb * Cfg::P2 + kp) * SF_TILE, &map_w2, bar_w, kp * 64, mb * 128);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  {  // per-channel constants and the weight side of the (dx,dy,dz) step (see sa_fused_kernel)
+    float* cst = reinterpret_cast<float*>(bp + Cfg::OFF_CONST);
+    for (int i = threadIdx.x; i < C1; i += Cfg::THREADS) cst[i] = p.b0[i];
+    for (int i = threadIdx.x; i < C2; i += Cfg::THREADS) cst[C1 + i] = p.b1[i];
+    for (int i = threadIdx.x; i < C3; i += Cfg::THREADS) cst[C1 + C2 + i] = p.b2[i];
+    for (int n = threadIdx.x; n < Cfg::WXYZ_ROWS; n += Cfg::THREADS) {
+      float w[3] = {0.f, 0.f, 0.f}, hi[3], lo[3];
+      if (n < C1) w[0] = p.wxyz[n * 4], w[1] = p.wxyz[n * 4 + 1], w[2] = p.wxyz[n * 4 + 2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        hi[i] = __bfloat162float(__float2bfloat16_rn(w[i]));
+        lo[i] = w[i] - hi[i];
+      }
+      uint8_t* wb = bp + Cfg::OFF_WXYZ;
+      *reinterpret_cast<uint4*>(wb + xyzoff(n, 0)) =
+          make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[0]), pack_bf16(hi[1], hi[2]), pack_bf16(lo[0], lo[1]));
+      *reinterpret_cast<uint4*>(wb + xyzoff(n, 1)) = make_uint4(pack_bf16(lo[2], 0.f), 0u, 0u, 0u);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *reinterpret_cast<uint32_t*>(bp + Cfg::OFF_BAR + 8 + 8 * NWG) + wg * 128;  // this group's columns
+
+#define SAR_BAR() asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory")
+  const float* cst = reinterpret_cast<const float*>(bp + Cfg::OFF_CONST);
+  uint8_t* xbuf = bp + Cfg::OFF_X + wg * Cfg::X_BYTES;
+  const uint32_t xaddr = base + Cfg::OFF_X + wg * Cfg::X_BYTES;
+  const uint32_t xyz_addr = base + Cfg::OFF_XYZ + wg * 4096;
+  int* src_row = reinterpret_cast<int*>(bp + Cfg::OFF_ROWS + wg * 512);
+  const int row = wq * 32 + lane;
+  const bool issuer = t128 == 32;  // lane 0 of the group's second warp issues the group's MMAs
+  uint32_t acc_phase = 0;
+  if (issuer) {
+    mbar_wait(bar_w, 0);  // the resident weights have landed
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+
+  for (long long tile = (long long)blockIdx.x * NWG + wg; tile < n_tiles; tile += (long long)gridDim.x * NWG) {
+    const long long g0 = tile * Cfg::GS;
+    // ---------------- gather (thread = row): neighbour index, hi/lo offsets, then the feature rows by cp.async
+    {
+      const int r = t128;
+      const long long g = g0 + r / NS;
+      const bool valid = g < p.groups;
+      int off = -1;
+      float d[3] = {0.f, 0.f, 0.f}, hi[3], lo[3];
+      if (valid) {
+        const int idx = p.gidx[g * NS + (r % NS)];
+        off = (int)(g / p.S) * p.N + idx;
+        const float* px = p.xyz + (long long)off * 3;
+        const float* pc = p.new_xyz + g * 3;
+        d[0] = fsub(px[0], pc[0]), d[1] = fsub(px[1], pc[1]), d[2] = fsub(px[2], pc[2]);
+      }
+      src_row[r] = off;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        hi[i] = __bfloat162float(__float2bfloat16_rn(d[i]));
+        lo[i] = d[i] - hi[i];
+      }
+      uint8_t* xb = bp + Cfg::OFF_XYZ + wg * 4096;
+      *reinterpret_cast<uint4*>(xb + xyzoff(r, 0)) =
+          make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], lo[0]), pack_bf16(lo[1], lo[2]), pack_bf16(hi[0], hi[1]));
+      *reinterpret_cast<uint4*>(xb + xyzoff(r, 1)) = make_uint4(pack_bf16(hi[2], 0.f), 0u, 0u, 0u);
+      if (D > 0) {
+        SAR_BAR();
+        constexpr int CPR = D / 8;  // 16-byte chunks per row
+#pragma unroll 2
+        for (int ch = t128; ch < 128 * CPR; ch += 128) {
+          const int rr = ch / CPR, c8 = ch % CPR;
+          const int o2 = src_row[rr];
+          const void* src = o2 >= 0 ? (const void*)(p.feats + (long long)o2 * D + c8 * 8) : (const void*)p.feats;
+          const int nbytes = o2 >= 0 ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xaddr + xoff(rr, c8 * 8)), "l"(src), "r"(nbytes)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    SAR_BAR();
+
+    // ---------------- layers 0 and 1: rows on M, one 128-column accumulator block ----------------
+#pragma unroll
+    for (int layer = 0; layer < 2; ++layer) {
+      const int PANELS = layer == 0 ? Cfg::P0 : Cfg::P1;
+      const uint32_t woff = layer == 0 ? Cfg::OFF_W0 : Cfg::OFF_W1;
+      const int COUT = layer == 0 ? C1 : C2;
+      const float* bias = cst + (layer == 0 ? 0 : C1);
+      if (issuer) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kp = 0; kp < PANELS; ++kp) {
+          const uint64_t da = desc_kmajor(xaddr + kp * SF_TILE), db = desc_kmajor(base + woff + kp * SF_TILE);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
+        }
+        if (layer == 0) umma_bf16(tmem, desc_kmajor_nosw(xyz_addr), desc_kmajor_nosw(base + Cfg::OFF_WXYZ), SF_IDESC, PANELS != 0);
+        umma_commit(bar_acc);
+      }
+      __syncwarp();
+      mbar_wait(bar_acc, acc_phase);
+      acc_phase ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < COUT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + c * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a = fmaxf(__uint_as_float(v[j]) + bias[c * 32 + j], 0.f);
+          float b = fmaxf(__uint_as_float(v[j + 1]) + bias[c * 32 + j + 1], 0.f);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(xbuf + xoff(row, c * 32 + i * 8)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      SAR_BAR();
+    }
+
+    // ---------------- layer 2: channels on M (128 per block), the tile's 128 rows on N ----------------
+    {
+      const float* b2s = cst + C1 + C2;
+      const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+      for (int mb = 0; mb < Cfg::MB3; ++mb) {
+        if (issuer) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int kp = 0; kp < Cfg::P2; ++kp) {
+            const uint64_t da = desc_kmajor(base + Cfg::OFF_W2 + (mb * Cfg::P2 + kp) * SF_TILE);
+            const uint64_t db = desc_kmajor(xaddr + kp * SF_TILE);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, SF_IDESC, (kp | k) != 0);
+          }
+          umma_commit(bar_acc);
+        }
+        __syncwarp();
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int ch = mb * 128 + wq * 32 + lane;
+        const float bias = b2s[ch];
+#pragma unroll 1
+        for (int g = 0; g < Cfg::GS; ++g) {
+          float m = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < NS / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + g * NS + c * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+          }
+          const long long grp = g0 + g;
+          if (grp < p.groups) p.out[grp * C3 + ch] = __float2bfloat16_rn(fmaxf(m + bias, 0.f));
+        }
+        // the next channel block / tile reuses the same TMEM columns: the whole group must have drained them
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        SAR_BAR();
+      }
+    }
+  }
+#undef SAR_BAR
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem - wg * 128), "r"(Cfg::TMEM_COLS));
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -515,6 +758,32 @@ int launch_sa(const SaParams& p, const void* w0, const void* w1, const void* w2,
   PFPP_RETURN_LAST();
 }
 
+template <int NS, int D, int C1, int C2, int C3, int NWG>
+int launch_sa_resident(const SaParams& p, const void* w0, const void* w1, const void* w2, cudaStream_t stream) {
+  using Cfg = SaResCfg<NS, D, C1, C2, C3, NWG>;
+  static_assert(D % 64 == 0 && C1 % 64 == 0 && C2 % 64 == 0 && C3 % 128 == 0, "panel-aligned channel counts");
+  CUtensorMap m0, m1, m2;
+  int rc = D > 0 ? weight_map(&m0, w0, C1, D, D) : weight_map(&m0, w1, C2, C1, C1);  // m0 unused when D == 0
+  if (rc) return rc;
+  rc = weight_map(&m1, w1, C2, C1, C1);
+  if (rc) return rc;
+  rc = weight_map(&m2, w2, C3, C2, C2);
+  if (rc) return rc;
+  auto kern = sa_resident_kernel<NS, D, C1, C2, C3, NWG>;
+  PFPP_ENSURE_SMEM(kern, Cfg::SMEM);
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const long long tiles = (p.groups + Cfg::GS - 1) / Cfg::GS;
+  long long grid = (tiles + NWG - 1) / NWG;
+  if (grid > n_sm) grid = n_sm;
+  kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, stream>>>(m0, m1, m2, p);
+  PFPP_RETURN_LAST();
+}
+
 }  // namespace
 
 static int sa_dispatch(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K,
@@ -525,11 +794,21 @@ static int sa_dispatch(int level, const float* xyz, const float* new_xyz, const 
   if (K == 0) return PFPP_OK;
   SaParams p{xyz, new_xyz, (const __nv_bfloat16*)feats, gidx, w0_xyz, b0, b1, b2, (__nv_bfloat16*)out, N, S,
              (long long)K * S, trace};
+  // Level 1 (32 KB of weights) runs the resident-weight kernel with 4 independent warpgroups per SM.  Level 2's
+  // weights (128 KB) also fit, but then only two 128-row tiles are in flight per SM and the kernel loses more
+  // latency hiding than it gains (measured 975 us vs 785 us), so levels 2 and 3 stream their weights.
+  // PFPP_SA_RESIDENT (tuning aid): bit 0 = level 1, bit 1 = level 2.
+  static const int resident = []() {
+    const char* e = getenv("PFPP_SA_RESIDENT");
+    return e ? atoi(e) : 1;
+  }();
   switch (level) {
     case 1:
+      if (resident & 1) return launch_sa_resident<32, 0, 64, 64, 128, 4>(p, w0_feat, w1, w2, stream);
       return launch_sa<32, 0, 64, 64, 128, 2, 1>(p, w0_feat, w1, w2, stream);
     case 2:
       PFPP_CHECK_ARG(feats && w0_feat);
+      if (resident & 2) return launch_sa_resident<64, 128, 128, 128, 256, 2>(p, w0_feat, w1, w2, stream);
       return launch_sa<64, 128, 128, 128, 256, 2, 2>(p, w0_feat, w1, w2, stream);
     case 3:
       PFPP_CHECK_ARG(feats && w0_feat);
