@@ -367,9 +367,9 @@ def main():
         peak_src = "nominal fp32 FFMA"
     def ncu_traffic(entry):
         """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-        `ncu --set full` capture of this command (profiles/r1d_*_full_summary.txt); None if there is no capture."""
-        fname = {"pfpp_sa_fused": "r1d_sa_full_summary.txt", "pfpp_gemm_bf16": "r1d_gemm_full_summary.txt",
-                 "pfpp_attention_tc": "r1d_attention_full_summary.txt"}.get(entry)
+        `ncu --set full` capture of this command (profiles/r1e_sa / r1d_gemm / r1e_attention _full_summary.txt); None if there is no capture."""
+        fname = {"pfpp_sa_fused": "r1e_sa_full_summary.txt", "pfpp_gemm_bf16": "r1d_gemm_full_summary.txt",
+                 "pfpp_attention_tc": "r1e_attention_full_summary.txt"}.get(entry)
         try:
             unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             tot, n = 0.0, 0
@@ -400,7 +400,7 @@ def main():
         "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
                      "frac": kernels[dom]["tflops"] / peak if peak else None, "traffic": ncu_traffic(dom),
-                     "traffic_note": "DRAM bytes per launch (read + write), mean over the launches of profiles/r1d_*_full_summary.txt",
+                     "traffic_note": "DRAM bytes per launch (read + write), mean over the launches captured in profiles/*_full_summary.txt",
                      "peak_source": peak_src,
                      "avg_launch_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["share_of_ddpm_step"],
                      "whole_step": {"algorithmic_tflop_per_ddpm_step": step_flops / 1e12,
