@@ -61,7 +61,9 @@ def parse():
 
 
 def workload_name(a):
-    return (f"config2: {a.frags} frags x {a.points} pts, {a.ddpm_steps} DDPM steps, 1 denoise pass + 1 verifier pass; "
+    tag = "config2" if (a.frags, a.points, a.ddpm_steps) == (20, 1000, 100) else (
+        "config5" if (a.frags, a.points, a.ddpm_steps) == (64, 2000, 250) else "custom")
+    return (f"{tag}: {a.frags} frags x {a.points} pts, {a.ddpm_steps} DDPM steps, 1 denoise pass + 1 verifier pass; "
             f"{a.batch} objects in flight per GPU")
 
 
@@ -76,11 +78,11 @@ def cpu_objects_per_sec(a, sample_steps):
     from oracle import verifier as ov
     from puzzlefusion_plusplus_b200 import synthetic
     torch.set_num_threads(os.cpu_count())
-    ck = synthetic.make_checkpoints(0)
-    obj = synthetic.make_object(1000, num_parts=a.frags, n_points=a.points)
+    P = max(20, a.frags)
+    ck = synthetic.make_checkpoints(0, max_parts=P)
+    obj = synthetic.make_object(1000, num_parts=a.frags, n_points=a.points, max_parts=P)
     sched = od.make_scheduler(a.ddpm_steps)
     g = torch.Generator().manual_seed(0)
-    P = 20
     x = torch.randn(P, 7, generator=g)
     t0 = time.perf_counter()
     with torch.no_grad():
@@ -260,15 +262,17 @@ def main():
     dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    ck = synthetic.make_checkpoints(0)
+    P = max(20, a.frags)  # fragment slots per object (config 5: 64; PE tables extended accordingly)
+    ck = synthetic.make_checkpoints(0, max_parts=P)
     n_str = max(1, min(a.streams, a.batch))
-    engines = [Engine(ck, num_inference_steps=a.ddpm_steps, precision=a.precision, device=dev, chunk_frags=a.chunk)
+    engines = [Engine(ck, num_inference_steps=a.ddpm_steps, precision=a.precision, device=dev, chunk_frags=a.chunk, max_parts=P)
                for _ in range(n_str)]
     eng = engines[0]
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_str)]
     # distinct objects per rank (weak scaling: per-GPU work fixed)
     n_unique = min(a.batch, 8)
-    uniq = [synthetic.make_object(2000 + rank * 64 + i, num_parts=a.frags, n_points=a.points) for i in range(n_unique)]
+    uniq = [synthetic.make_object(2000 + rank * 64 + i, num_parts=a.frags, n_points=a.points, max_parts=P)
+            for i in range(n_unique)]
     objects = [uniq[i % n_unique] for i in range(a.batch)]
     seeds = [rank * 10007 + i for i in range(a.batch)]
     parts = [list(range(i, a.batch, n_str)) for i in range(n_str)]  # object indices per stream
@@ -334,11 +338,11 @@ def main():
     o = objects[0]
     h2d = a.batch * sum(int(v.numel() * v.element_size()) for k, v in o.items() if torch.is_tensor(v) and k in (
         "part_pcs", "part_scale", "part_trans", "part_rots", "part_pcs_by_area"))
-    d2h = a.batch * (20 * 7 * 4 * 2 + 190 * 4)
+    d2h = a.batch * (P * 7 * 4 * 2 + P * (P - 1) // 2 * 4)  # poses (x, final) + one logit per fragment pair
 
     # ---- kernel probe: eager DDPM steps of the whole batch on one stream, events around every launch ----
     probe_steps = 3
-    eng_p = Engine(ck, num_inference_steps=a.ddpm_steps, precision=a.precision, device=dev, chunk_frags=a.chunk)
+    eng_p = Engine(ck, num_inference_steps=a.ddpm_steps, precision=a.precision, device=dev, chunk_frags=a.chunk, max_parts=P)
     runner = BatchRunner(eng_p, objects, max_iters=1, noise=PerObjectNoise(dev, seeds, a.ddpm_steps), trajectory=False,
                          use_graph=False)
     runner.begin_iteration()

@@ -148,7 +148,8 @@ int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_off, int v_o
  * [M, 3C] (q | k | v, head h at columns h*64), head_dim 64, one CTA per (segment, head); S = QK^T and
  * O = PV run as tcgen05.mma with fp32 accumulators in TMEM, operands by TMA, online softmax.
  * block == 0: global attention (attention.py:84 with the key mask): every token of a segment (one object's
- *   valid fragments, <= 512 tokens) attends to the whole segment.
+ *   valid fragments) attends to the whole segment.  Segments of <= 512 tokens keep K/V resident in shared memory
+ *   (one CTA per segment and head); longer segments run two query tiles per CTA and stream K/V through a ring.
  * block  > 0: the block-diagonal local attention (attention.py:79 with self_mask,
  *   denoiser_transformer.py:158-166): tokens attend inside aligned blocks of `block` tokens; a segment holds
  *   up to 4 tiles of floor(128/block) blocks (block 25: 125-token tiles, segments <= 500 tokens) and

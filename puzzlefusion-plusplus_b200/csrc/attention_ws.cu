@@ -48,7 +48,7 @@ constexpr uint32_t AW_COL_S = 0, AW_COL_O = 256;
 constexpr float AW_LAZY = 8.0f;  // log2 units
 
 // barrier slots (8 bytes each); per-group barriers are indexed [w], per-group-per-buffer ones [2 w + buf]
-enum { B_Q = 0, B_QFREE = 2, B_K = 4, B_V = 8, B_S = 12, B_SFREE = 16, B_P = 20, B_PV = 24, B_TOK = 28, B_COUNT = 30 };
+enum { B_Q = 0, B_QFREE = 2, B_K = 4, B_V = 8, B_S = 12, B_SFREE = 16, B_P = 20, B_PV = 24, B_TOK = 28, B_KFREE = 30, B_VFREE = 34, B_COUNT = 38 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -243,12 +243,22 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
   const uint32_t bars = base + AW_OFF_BAR;
   const uint32_t tmem_slot = bars + B_COUNT * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt = min(AW_MAXT, (len + tile_stride - 1) / tile_stride);  // query tiles == key tiles
+  // Short segments (<= 4 tiles, grid.z == 1): K/V of the whole segment stay resident, group w runs query tiles
+  // w and w + 2.  Long segments (global attention only, grid.z > 1): CTA z runs query tiles 2z and 2z + 1 (one per
+  // group) and streams the segment's key tiles through the 4 K and 4 V slots as a ring (slot = tile & 3).
+  const bool long_mode = gridDim.z > 1;
+  const int nkt = (len + tile_stride - 1) / tile_stride;       // tiles of the segment
+  const int nt = long_mode ? nkt : min(AW_MAXT, nkt);          // query tiles == key tiles that are processed
+  const int jq_step = long_mode ? (1 << 20) : 2;               // long mode: one query tile per group
+  const int jq_base = long_mode ? 2 * (int)blockIdx.z : 0;     // group w starts at query tile jq_base + w
+  if (jq_base >= nt) return;
   // steps (64 keys) of key tile kb that hold at least one key of the segment
   auto tile_steps = [&](int kb) { return (min(tile_stride, len - kb * tile_stride) + AW_STEP - 1) / AW_STEP; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + 8 * i, ((i >= B_SFREE && i < B_PV) || i >= B_TOK) ? 128u : 1u);
+    const uint32_t n_issuers = jq_base + 1 < nt ? 2u : 1u;  // consumers of a K/V ring slot (long mode)
+    for (int i = 0; i < B_COUNT; ++i)
+      mbar_init(bars + 8 * i, i >= B_KFREE ? n_issuers : (((i >= B_SFREE && i < B_PV) || i >= B_TOK) ? 128u : 1u));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 10) {
@@ -265,6 +275,23 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const int qc = h * AW_D, kc = C + h * AW_D, vc = 2 * C + h * AW_D;
+      if (long_mode) {
+        for (int w = 0; w < 2 && jq_base + w < nt; ++w) {
+          mbar_expect_tx(bars + 8 * (B_Q + w), AW_TILE);
+          tma_load_2d(base + AW_OFF_Q + w * AW_TILE, &map, bars + 8 * (B_Q + w), qc, st + (jq_base + w) * tile_stride);
+        }
+        for (int kb = 0; kb < nt; ++kb) {
+          const int slot = kb & 3;
+          // a slot is refilled once every S (K) / PV (V) product of both groups that read tile kb - 4 has completed
+          if (kb >= 4) mbar_wait(bars + 8 * (B_KFREE + slot), ((kb >> 2) - 1) & 1);
+          mbar_expect_tx(bars + 8 * (B_K + slot), AW_TILE);
+          tma_load_2d(base + AW_OFF_K + slot * AW_TILE, &map, bars + 8 * (B_K + slot), kc, st + kb * tile_stride);
+          if (kb >= 4) mbar_wait(bars + 8 * (B_VFREE + slot), ((kb >> 2) - 1) & 1);
+          mbar_expect_tx(bars + 8 * (B_V + slot), AW_TILE);
+          tma_load_2d(base + AW_OFF_V + slot * AW_TILE, &map, bars + 8 * (B_V + slot), vc, st + kb * tile_stride);
+        }
+        AW_TRACE(2);
+      } else {
       mbar_expect_tx(bars + 8 * (B_Q + 0), AW_TILE);
       tma_load_2d(base + AW_OFF_Q, &map, bars + 8 * (B_Q + 0), qc, st);
       mbar_expect_tx(bars + 8 * (B_K + 0), AW_TILE);
@@ -296,24 +323,25 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
           tma_load_2d(base + AW_OFF_Q + w * AW_TILE, &map, bars + 8 * (B_Q + w), qc, st + (w + 2) * tile_stride);
         }
       }
+      }  // short mode
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ MMA issuer of group w
     const int w = warp - 8;
-    if (lane == 0 && w < nt) {
+    if (lane == 0 && jq_base + w < nt) {
       // S cursor (tile jq, key tile kb, half hf) runs two steps ahead of the PV cursor
-      int s_jq = w, s_kb = block ? w : 0, s_hf = 0, s_n = 0;
+      int s_jq = jq_base + w, s_kb = block ? s_jq : 0, s_hf = 0, s_n = 0, s_job = 0;
       bool s_more = true;
       auto issue_s = [&]() {
         const int kb_last = block ? s_jq : nt - 1;
         if (s_n >= 2) mbar_wait(bars + 8 * (B_SFREE + 2 * w + (s_n & 1)), ((s_n >> 1) - 1) & 1);
         if (s_hf == 0) {
-          if (s_kb == (block ? s_jq : 0)) mbar_wait(bars + 8 * (B_Q + w), (s_jq >> 1) & 1);
-          mbar_wait(bars + 8 * (B_K + s_kb), 0);
+          if (s_kb == (block ? s_jq : 0)) mbar_wait(bars + 8 * (B_Q + w), s_job & 1);
+          mbar_wait(bars + 8 * (B_K + (s_kb & 3)), (s_kb >> 2) & 1);
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dq = desc_kmajor(base + AW_OFF_Q + w * AW_TILE);
-        const uint64_t dk = desc_kmajor(base + AW_OFF_K + s_kb * AW_TILE + s_hf * (AW_TILE / 2));
+        const uint64_t dk = desc_kmajor(base + AW_OFF_K + (s_kb & 3) * AW_TILE + s_hf * (AW_TILE / 2));
         const uint32_t d = tmem + AW_COL_S + (2 * w + (s_n & 1)) * AW_STEP;
 #pragma unroll
         for (int k = 0; k < AW_D / 16; ++k) umma_bf16(d, dq + 2 * k, dk + 2 * k, AW_IDESC_S, k != 0);
@@ -322,37 +350,42 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
         ++s_n;
         if (s_hf + 1 < tile_steps(s_kb)) {
           ++s_hf;
-        } else if (s_kb < kb_last) {
-          ++s_kb;
-          s_hf = 0;
-        } else if (s_jq + 2 < nt) {
-          umma_commit(bars + 8 * (B_QFREE + w));  // last S of this query tile: its Q slot may be refilled
-          s_jq += 2;
-          s_kb = block ? s_jq : 0;
-          s_hf = 0;
         } else {
-          s_more = false;
+          if (long_mode) umma_commit(bars + 8 * (B_KFREE + (s_kb & 3)));  // this group is done with K tile s_kb
+          if (s_kb < kb_last) {
+            ++s_kb;
+            s_hf = 0;
+          } else if (s_jq + jq_step < nt) {
+            umma_commit(bars + 8 * (B_QFREE + w));  // last S of this query tile: its Q slot may be refilled
+            s_jq += jq_step;
+            ++s_job;
+            s_kb = block ? s_jq : 0;
+            s_hf = 0;
+          } else {
+            s_more = false;
+          }
         }
       };
       issue_s();
       if (s_more) issue_s();
       int p_n = 0;
-      for (int jq = w; jq < nt; jq += 2) {
+      for (int jq = jq_base + w; jq < nt; jq += jq_step) {
         const int kb_first = block ? jq : 0, kb_last = block ? jq : nt - 1;
         for (int kb = kb_first; kb <= kb_last; ++kb) {
           const int nh = tile_steps(kb);
           for (int hf = 0; hf < nh; ++hf, ++p_n) {
             const int b = p_n & 1;
             mbar_wait(bars + 8 * (B_P + 2 * w + b), (p_n >> 1) & 1);
-            if (hf == 0) mbar_wait(bars + 8 * (B_V + kb), 0);
+            if (hf == 0) mbar_wait(bars + 8 * (B_V + (kb & 3)), (kb >> 2) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t pa = base + AW_OFF_P + (2 * w + b) * AW_TILE;
-            const uint32_t va = base + AW_OFF_V + kb * AW_TILE + hf * (AW_TILE / 2);
+            const uint32_t va = base + AW_OFF_V + (kb & 3) * AW_TILE + hf * (AW_TILE / 2);
 #pragma unroll
             for (int k = 0; k < AW_STEP / 16; ++k)
               umma_bf16(tmem + AW_COL_O + w * AW_D, desc_kmajor(pa) + 2 * k, desc_mnmajor(va + k * 2048), AW_IDESC_O,
                         !(kb == kb_first && hf == 0) || k != 0);
             umma_commit(bars + 8 * (B_PV + 2 * w + b));
+            if (long_mode && hf + 1 == nh) umma_commit(bars + 8 * (B_VFREE + (kb & 3)));  // done with V tile kb
             if (s_more) issue_s();
           }
         }
@@ -370,15 +403,15 @@ __global__ void __launch_bounds__(AW_THREADS, 1)
     // time at half rate each and then idle in their TMEM-load / max / barrier phases at the same time as well.
     // Group 0 runs tiles 0,2 and group 1 tiles 1,3 with the same number of steps per tile, so group 1 never has
     // more steps than group 0.
-    const bool take_turns = (block == 0) && nt > 1;
+    const bool take_turns = (block == 0) && jq_base + 1 < nt;
     int steps_other = 0;  // total steps of the other group
     if (take_turns) {
       int per_tile = 0;
       for (int kb = 0; kb < nt; ++kb) per_tile += tile_steps(kb);
-      steps_other = per_tile * ((nt - (1 - w) + 1) / 2);
+      steps_other = long_mode ? per_tile : per_tile * ((nt - (1 - w) + 1) / 2);
     }
     const int blk_lo = block ? (row / block) * block : 0;  // first key (tile-relative) of this row's block
-    for (int jq = w; jq < nt; jq += 2) {
+    for (int jq = jq_base + w; jq < nt; jq += jq_step) {
       const int tile_len = min(tile_stride, len - jq * tile_stride);
       const int kb_first = block ? jq : 0, kb_last = block ? jq : nt - 1;
       float m_used = -INFINITY, l = 0.f;
@@ -527,7 +560,9 @@ static int attention_launch(const void* qkv, long long M, int ld, int C, const i
   PFPP_CHECK_ARG(qkv && seg_start && seg_len && out && heads > 0 && C == heads * AW_D);
   PFPP_CHECK_ARG(block >= 0 && block <= AW_TK);
   const int tile_stride = block ? (AW_TK / block) * block : AW_TK;
-  PFPP_CHECK_ARG(max_len <= AW_MAXT * tile_stride && (ld % 8) == 0 && (ldo % 8) == 0 && ((uintptr_t)qkv & 15) == 0 &&
+  // segments of more than 4 tiles: global attention only (K/V streamed through the 4-slot ring, 2 query tiles per CTA)
+  const bool long_segments = max_len > AW_MAXT * tile_stride;
+  PFPP_CHECK_ARG((!long_segments || block == 0) && (ld % 8) == 0 && (ldo % 8) == 0 && ((uintptr_t)qkv & 15) == 0 &&
                  ((uintptr_t)out & 15) == 0);
   if (n_segments == 0 || max_len <= 0 || M == 0) return PFPP_OK;
   auto fn = encode_fn();
@@ -542,7 +577,7 @@ static int attention_launch(const void* qkv, long long M, int ld, int C, const i
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return PFPP_EINVAL;
   PFPP_ENSURE_SMEM(attention_ws_kernel, AW_SMEM_BYTES);
-  dim3 grid(heads, n_segments);
+  dim3 grid(heads, n_segments, long_segments ? (pfpp_cdiv(max_len, AW_TK) + 1) / 2 : 1);
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)AW_D);
   attention_ws_kernel<<<grid, AW_THREADS, AW_SMEM_BYTES, stream>>>(map, seg_start, seg_len, C, scale_log2e, block,
                                                                   tile_stride, (__nv_bfloat16*)out, ldo, trace);

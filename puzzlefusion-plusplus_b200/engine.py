@@ -59,7 +59,7 @@ class Engine:
         self.den = DenoiserWeights(ckpt["denoiser"], self.device, self.bf16, num_layers, self.sched.timesteps)
         self.ver = VerifierWeights(ckpt["verifier"], self.device, verifier_layers) if "verifier" in ckpt else None
         self.C = self.den.C
-        self.tc_attention = True  # tcgen05 global attention in bf16 mode (segments <= 512 tokens)
+        self.tc_attention = True  # tcgen05 attention in bf16 mode (segments > 512 tokens stream K/V through a ring)
         self.fused_sa = True     # fused gather + 3-layer MLP + max tcgen05 kernel in bf16 mode
         self.local_tiles = 4     # 125-token tiles (5 fragments) per local-attention CTA, two per softmax group
         self._ws = {}
@@ -217,7 +217,7 @@ class Engine:
                 call("pfpp_layernorm", h.data_ptr(), None, None, None, mod.data_ptr(), frag_tidx.data_ptr(), L, M, C, bf,
                      ln.data_ptr(), None)
                 self.gemm(ln, C, lw[name + ".qkv"], qkv, 3 * C, M)
-                if self.bf16 and which == 1 and mlen <= 512 and D == 64 and self.tc_attention:
+                if self.bf16 and which == 1 and D == 64 and self.tc_attention:
                     call("pfpp_attention_tc", qkv.data_ptr(), M, 3 * C, C, segs[0].data_ptr(), segs[1].data_ptr(), nseg,
                          mlen, H, 0, ao.data_ptr(), C)
                 elif self.bf16 and which == 0 and D == 64 and self.tc_attention and 5 * L <= 128:

@@ -354,12 +354,14 @@ def test_merge_filter_matches_oracle(lib):
 
 
 @pytest.mark.parametrize("qscale", [1.0, 6.0])
-@pytest.mark.parametrize("lens", [[500], [500, 325, 50, 128, 129], [25, 512, 257], [384, 1, 255, 256, 475]])
+@pytest.mark.parametrize("lens", [[500], [500, 325, 50, 128, 129], [25, 512, 257], [384, 1, 255, 256, 475], [1600],
+                                  [513, 700, 128, 1025], [1600, 40, 897]])
 def test_attention_tcgen05(lib, lens, qscale):
     """tcgen05 global attention (bf16 operands, fp32 softmax/accumulation) vs torch SDPA on the same
     bf16-rounded q/k/v: tolerance 2e-2 absolute (bf16 P and bf16 output rounding).  qscale 6 gives
     scores of magnitude ~50, so the running maximum jumps between key blocks and the lazy rescale of
-    the O accumulator is exercised."""
+    the O accumulator is exercised.  Segments longer than 512 tokens (config 5: 64 fragments = 1600 tokens) take the
+    long mode: two query tiles per CTA, K/V streamed through the 4-slot ring."""
     H, D = 8, 64
     C = H * D
     M = sum(lens)
