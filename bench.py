@@ -131,8 +131,10 @@ def run_reference(a, rank):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region, in-process through NVML (nvidia_ml_py).
+    Forking `nvidia-smi` from this process instead costs 50-100 ms of host stall per sample (page tables of a
+    process with a CUDA context) and showed up as random slow steps in the timed region."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.rows, self.stop = [], False
@@ -142,15 +144,34 @@ class ClockSampler:
     def _run(self):
         if self.index is None:
             return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # map the CUDA ordinal to the NVML handle through the PCI bus id (CUDA_VISIBLE_DEVICES may reorder)
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        h = hi
+                        break
+            h = h or pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(mx), int(rs)))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def __enter__(self):
         self.th.start()
@@ -163,12 +184,10 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        sm = [r[0] for r in self.rows]
+        reasons = [n for n, bit in self.REASONS if any(r[2] & bit for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(r[1] for r in self.rows), "reasons": reasons,
+                "samples": len(self.rows), "source": "NVML, sampled every 0.1 s during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -307,15 +326,30 @@ def main():
     for _ in range(a.warmup):
         one_step(make_states())
     states = [make_states() for _ in range(a.steps)]
+    # Host runtime policy for the timed regions (as a serving process would run): long-lived host objects
+    # (checkpoints, objects, pre-built states) are frozen out of the cyclic GC's working set and automatic
+    # collection is off while batches are in flight (re-enabled at the end).  With the collector on, random batch
+    # steps take 40-170 ms longer (measured, `ms_each_step`); PFPP_BENCH_GC=1 keeps it on.
+    import gc
+    gc.collect()
+    gc.freeze()
+    host_gc = "on" if os.environ.get("PFPP_BENCH_GC") else "frozen + disabled during the timed regions"
+    if host_gc != "on":
+        gc.disable()
     barrier()
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(None if a.no_clocks else local) as clk:
         e0.record()
+        step_ev = []
         for k in range(a.steps):
             metrics = one_step(states[k])
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            step_ev.append(ev)
         e1.record()
         barrier()
+    per_step_ms = [a_.elapsed_time(b_) for a_, b_ in zip([e0] + step_ev[:-1], step_ev)]
     elapsed_ms = e0.elapsed_time(e1)
     launches = _lib.launch_count - launches0
     t = torch.tensor([elapsed_ms], device=dev)
@@ -395,9 +429,9 @@ def main():
     ddpm_ms_timed = elapsed_ms / a.steps / a.ddpm_steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": elapsed_ms / a.steps, "ms_each_step": [round(v, 1) for v in per_step_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "precision_mode": a.precision, "streams": n_str,
+        "config": {"workload": workload_name(a), "precision_mode": a.precision, "streams": n_str, "host_gc": host_gc,
                    "l2": "per-step working set (activations of one fragment chunk) exceeds L2; inputs differ per step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -415,6 +449,7 @@ def main():
                              "replays CUDA graphs); FLOPs are algorithmic (masked work not counted)"},
         "kernels": kernels,
     }
+    gc.enable()
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             v, t_step, t_verify = cpu_objects_per_sec(a, a.cpu_sample_steps)

@@ -12,6 +12,7 @@ by-area cloud, no re-noising between outer iterations, index-aligned Chamfer in 
 Rows of ``x`` that belong to padded or merged-away slots are never read by any valid output (App. C.9,
 C.10) and are left untouched here.
 """
+import gc
 import itertools
 
 import networkx as nx
@@ -20,7 +21,7 @@ import torch
 
 from . import _lib
 from ._lib import call
-from .pose_utils import affine, compose_params, compose_params_steps, quat_to_matrix
+from .pose_utils import affine, compose_params_batch, compose_params_steps, quat_to_matrix
 
 
 class GlobalTorchNoise:
@@ -100,14 +101,17 @@ class BatchState:
         self.B, self.P = len(objects), engine.P
         B, P = self.B, self.P
         self.N = objects[0]["part_pcs"].shape[1]
-        f32 = dict(dtype=torch.float32, device=dev)
-        self.part_pcs = torch.stack([o["part_pcs"] for o in objects]).to(**f32).reshape(B * P, self.N, 3).contiguous()
-        self.scale = torch.stack([o["part_scale"].reshape(P) for o in objects]).to(**f32).reshape(B * P).contiguous()
-        self.gt = torch.stack([torch.cat([o["part_trans"], o["part_rots"]], -1) for o in objects]).to(**f32)
+        # inputs go through the engine's pinned staging buffers (asynchronous H2D on the current stream)
+        up = getattr(engine, "upload", None) or (
+            lambda name, ts: torch.stack(ts).to(dtype=torch.float32, device=dev))  # engine stand-ins in unit tests
+        self.part_pcs = up("part_pcs", [o["part_pcs"] for o in objects]).reshape(B * P, self.N, 3)
+        scale_h = torch.stack([o["part_scale"].reshape(P) for o in objects]).float()
+        self.scale = up("scale", [o["part_scale"].reshape(P) for o in objects]).reshape(B * P)
+        self.gt = up("gt", [torch.cat([o["part_trans"], o["part_rots"]], -1) for o in objects])
         self.num_parts = [int(o["num_parts"]) for o in objects]
         self.valid = np.stack([np.asarray(o["part_valids"]) > 0 for o in objects])  # host mirror [B,P]
         self.ref = np.stack([np.asarray(o["ref_part"]).astype(bool) for o in objects])  # host mirror [B,P]
-        self.scale_host = self.scale.cpu().reshape(B, P).clone()
+        self.scale_host = scale_h.reshape(B, P).clone()
         self.pivot = [list(range(n)) for n in self.num_parts]
         self.node_valid = [[True] * n for n in self.num_parts]
         self.init_pose = [[None] * n for n in self.num_parts]
@@ -303,12 +307,7 @@ class BatchRunner:
         st, e = self.st, self.e
         B, P = st.B, e.P
         x_host = self.x.cpu().reshape(B, P, 7)
-        pred_t = torch.zeros(B, P, 3)
-        pred_r = torch.zeros(B, P, 4)
-        for b in range(B):
-            tr, qr = compose_params(x_host[b], st.pivot[b], st.init_pose[b])
-            pred_t[b, :st.num_parts[b]] = tr
-            pred_r[b, :st.num_parts[b]] = qr
+        pred_t, pred_r = compose_params_batch(x_host, st.pivot, st.init_pose, st.num_parts)
         return {"x": x_host, "pred_trans": pred_t, "pred_rots": pred_r,
                 "trajectory": [torch.cat(t) if t else torch.zeros(0) for t in self.traj], "iters": self.iters,
                 "pivots": st.pivot, "ref_part": torch.as_tensor(st.ref), "part_valids": torch.as_tensor(st.valid)}
@@ -322,6 +321,22 @@ def run_interleaved(runners, streams=None):
     for s_ in streams:
         if s_ is not cur:
             s_.wait_stream(cur)
+    # no cyclic-GC pauses while kernels are being enqueued (a full collection costs tens of ms and stalls the GPU
+    # queue); the small host objects of this loop are reclaimed after the run
+    gc_was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        _advance(runners, streams)
+    finally:
+        if gc_was_enabled:
+            gc.enable()
+    for s_ in streams:
+        if s_ is not cur:
+            cur.wait_stream(s_)
+    return [r.result() for r in runners]
+
+
+def _advance(runners, streams):
     while True:
         live = []
         for r, s_ in zip(runners, streams):
@@ -337,10 +352,6 @@ def run_interleaved(runners, streams=None):
         for r, s_ in live:
             with torch.cuda.stream(s_):
                 r.end_iteration()
-    for s_ in streams:
-        if s_ is not cur:
-            cur.wait_stream(s_)
-    return [r.result() for r in runners]
 
 
 def run_batch(engine, objects, max_iters, threshold=0.9, noise=None, merge=True, record=None, trajectory=True,
@@ -376,22 +387,32 @@ def _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshol
     call("pfpp_edge_features", st.by_area_T.data_ptr(), st.pair_src.data_ptr(), st.pair_tgt.data_ptr(),
          st.e_start.data_ptr(), st.e_len.data_ptr(), st.e_row.data_ptr(), st.n_edges, max(st.max_pairs, 1), n_rows,
          feat.data_ptr())
-    tok_row, tok_i, tok_j, seg_start, seg_len = [], [], [], [], []
-    for b in active:
-        seg_start.append(len(tok_row))
-        n = st.num_parts[b]
-        for e, (i, j) in enumerate(st.tri_list):
-            if i < n and j < n:
-                tok_row.append(b * st.E_full + e)
-                tok_i.append(i)
-                tok_j.append(j)
-        seg_len.append(len(tok_row) - seg_start[-1])
-    tok_row, tok_i, tok_j, seg_start_d, seg_len_d = i32(tok_row), i32(tok_i), i32(tok_j), i32(seg_start), i32(seg_len)
-    logits = engine.verifier_logits(feat, tok_row, tok_i, tok_j, seg_start_d, seg_len_d, max(seg_len), n_rows)
+    # packed valid-edge tokens of the active objects: depends only on (active, num_parts) -> cached on the state
+    key = tuple(active)
+    if getattr(st, "_tok_key", None) != key:
+        tri = np.asarray(st.tri_list, dtype=np.int64)  # [E_full, 2]
+        rows, ii, jj, seg_start, seg_len = [], [], [], [], []
+        pos = 0
+        for b in active:
+            n = st.num_parts[b]
+            e = np.nonzero((tri[:, 0] < n) & (tri[:, 1] < n))[0]
+            rows.append(b * st.E_full + e)
+            ii.append(tri[e, 0])
+            jj.append(tri[e, 1])
+            seg_start.append(pos)
+            seg_len.append(len(e))
+            pos += len(e)
+        st._tok = (i32(np.concatenate(rows)), i32(np.concatenate(ii)), i32(np.concatenate(jj)), i32(seg_start), i32(seg_len),
+                   max(seg_len))
+        st._tok_key = key
+    tok_row, tok_i, tok_j, seg_start_d, seg_len_d, max_seg = st._tok
+    logits = engine.verifier_logits(feat, tok_row, tok_i, tok_j, seg_start_d, seg_len_d, max_seg, n_rows)
     logits_h = logits.cpu().reshape(B, st.E_full)  # D2H (syncs)
     if record is not None:
         record.append({"verify": True, "edge_features": feat.clone().reshape(B, st.E_full, 7), "logits": logits_h.clone()})
     pred = torch.sigmoid(logits_h) > threshold  # auto_aggl.py:204-205 (edge validity applied below)
+    pred_np = pred.numpy()
+    tri_np = np.asarray(st.tri_list, dtype=np.int64)
     # reference_gt_and_rots = x.clone() (auto_aggl.py:222) for active objects
     ref_pose.copy_(x)
 
@@ -402,8 +423,8 @@ def _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshol
         ref_idx = [p for p in range(P) if st.ref[b, p]]
         st.classified[b, ref_idx] = True
         larger = st.valid[b] & (st.scale_host[b].numpy() > 0.05)
-        accepted = [(i, j) for e, (i, j) in enumerate(st.tri_list)
-                    if i < n and j < n and bool(pred[b, e])]
+        acc_e = np.nonzero(pred_np[b] & (tri_np[:, 0] < n) & (tri_np[:, 1] < n))[0]
+        accepted = [st.tri_list[e] for e in acc_e]
         new_ref = []
         for (i, j) in accepted:
             i_ref, j_ref = i in ref_idx, j in ref_idx

@@ -69,3 +69,31 @@ def compose_params_steps(xs, pivots, init_poses):
     composed = mats @ init
     mats = torch.where(has.view(1, n, 1, 1), composed, mats)
     return torch.cat([mats[..., :3, 3], matrix_to_quat(mats[..., :3, :3])], -1)
+
+
+def compose_params_batch(x, pivots, init_poses, num_parts):
+    """compose_params for a whole batch in one shot: x [B,P,7] CPU, per-object pivot / init_pose lists ->
+    pred_trans [B,P,3], pred_rots [B,P,4] (rows >= num_parts[b] are zero)."""
+    B, P = x.shape[0], x.shape[1]
+    pv = torch.zeros(B, P, dtype=torch.long)
+    has = torch.zeros(B, P, dtype=torch.bool)
+    node = torch.zeros(B, P, dtype=torch.bool)
+    init = torch.eye(4).repeat(B, P, 1, 1)
+    for b in range(B):
+        n = num_parts[b]
+        pv[b, :n] = torch.as_tensor(pivots[b][:n], dtype=torch.long)
+        node[b, :n] = True
+        for i, m in enumerate(init_poses[b][:n]):
+            if m is not None:
+                has[b, i] = True
+                init[b, i] = m
+    xp = torch.gather(x, 1, pv.unsqueeze(-1).expand(B, P, 7))
+    mats = torch.zeros(B, P, 4, 4)
+    mats[:, :, :3, :3] = quat_to_matrix(xp[..., 3:])
+    mats[:, :, :3, 3] = xp[..., :3]
+    mats[:, :, 3, 3] = 1.0
+    if bool(has.any()):
+        mats = torch.where(has.view(B, P, 1, 1), mats @ init, mats)
+    trans = mats[..., :3, 3] * node.unsqueeze(-1)
+    quat = matrix_to_quat(mats[..., :3, :3]) * node.unsqueeze(-1)
+    return trans, quat
