@@ -139,36 +139,38 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.stop = [], False
         self.index = index
+        self.h = self.nv = None
+        if index is not None:
+            try:  # NVML is initialised here, before the timed region: nvmlInit + import cost tens of ms of host time
+                import pynvml
+                pynvml.nvmlInit()
+                h = None
+                bus = getattr(torch.cuda.get_device_properties(index), "pci_bus_id", None)
+                if bus is not None:  # CUDA_VISIBLE_DEVICES may reorder: match the CUDA device by PCI bus id
+                    for i in range(pynvml.nvmlDeviceGetCount()):
+                        hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                        if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                            h = hi
+                            break
+                self.h = h or pynvml.nvmlDeviceGetHandleByIndex(index)
+                self.nv = pynvml
+                self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            except Exception:
+                self.h = None
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        if self.index is None:
+        if self.h is None:
             return
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            # map the CUDA ordinal to the NVML handle through the PCI bus id (CUDA_VISIBLE_DEVICES may reorder)
-            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
-                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
-            h = None
-            if bus is not None:
-                for i in range(pynvml.nvmlDeviceGetCount()):
-                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
-                    if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
-                        h = hi
-                        break
-            h = h or pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        except Exception:
-            return
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        nv, h = self.nv, self.h
         while not self.stop:
             try:
-                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
-                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
-                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append((float(sm), float(mx), int(rs)))
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), self.mx, int(rs)))
             except Exception:
                 pass
             time.sleep(0.1)
@@ -302,15 +304,22 @@ def main():
         return [BatchState(engines[i], [objects[j] for j in parts[i]]) for i in range(n_str)]
 
     def one_step(resident_states=None):
+        t_0 = time.perf_counter()
         runners = [BatchRunner(engines[i], [objects[j] for j in parts[i]], max_iters=1,
                                noise=PerObjectNoise(dev, [seeds[j] for j in parts[i]], a.ddpm_steps), trajectory=False,
                                state=None if resident_states is None else resident_states[i], verify_last=True,
                                use_graph=not a.no_graph)
                    for i in range(n_str)]
+        t_a = time.perf_counter()
         outs = run_interleaved(runners, streams)
+        t_b = time.perf_counter()
         out = {k: torch.cat([outs[i][k] for i in range(n_str)]) for k in ("pred_trans", "pred_rots")}
         order = [j for pl in parts for j in pl]
         m = object_metrics(out, [objects[j] for j in order]).to(dev)  # [B,4] per-object metric block
+        if os.environ.get("PFPP_BENCH_PHASES"):
+            torch.cuda.synchronize()
+            print(f"[phases] runners {1e3 * (t_a - t_0):.1f} ms, loop {1e3 * (t_b - t_a):.1f} ms, metrics "
+                  f"{1e3 * (time.perf_counter() - t_b):.1f} ms", file=sys.stderr)
         if world > 1:
             gathered = torch.empty(world * m.shape[0], m.shape[1], device=dev)
             dist.all_gather_into_tensor(gathered, m)
@@ -337,9 +346,11 @@ def main():
     if host_gc != "on":
         gc.disable()
     barrier()
+    sampler = ClockSampler(None if a.no_clocks else local)
+    barrier()
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(None if a.no_clocks else local) as clk:
+    with sampler as clk:
         e0.record()
         step_ev = []
         for k in range(a.steps):
