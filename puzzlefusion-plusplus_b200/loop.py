@@ -135,32 +135,47 @@ class BatchState:
         base, pos = 0, 0
         for b, o in enumerate(objects):
             pts.append(o["part_pcs_by_area"].float())
-            n_pcs = np.asarray(o["n_pcs"]).astype(np.int64)
-            cs = np.concatenate([[0], np.cumsum(n_pcs)])
+            m = o.get("_pfpp_matching")
+            if m is None:
+                # object-local tables (offsets relative to the object's by-area cloud / edge-row block); they depend
+                # only on the object, so they are built once and kept on the object dict
+                n_pcs = np.asarray(o["n_pcs"]).astype(np.int64)
+                cs = np.concatenate([[0], np.cumsum(n_pcs)])
+                crit = np.asarray(o["critical_pcs_idx"]).astype(np.int64)
+                edges = np.asarray(o["edges"]).reshape(-1, 2)
+                src_l, tgt_l, len_l, row_l = [], [], [], []
+                for e in range(edges.shape[0]):
+                    idx2, idx1 = int(edges[e, 0]), int(edges[e, 1])
+                    corr = np.asarray(o["correspondences"][e]).reshape(-1, 2)
+                    src_l.append(cs[idx1] + crit[cs[idx1] + corr[:, 0]])
+                    tgt_l.append(cs[idx2] + crit[cs[idx2] + corr[:, 1]])
+                    len_l.append(corr.shape[0])
+                    row_l.append(tri[(idx1, idx2)])
+                cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, dtype=np.int64)  # noqa: E731
+                m = (cs, cat(src_l), cat(tgt_l), np.asarray(len_l, dtype=np.int64), np.asarray(row_l, dtype=np.int64), P)
+                o["_pfpp_matching"] = m
+            cs, src, tgt, lens, rows, p_built = m
+            assert p_built == P, "object tables were built for another slot count"
             self.area_base.append(base)
             self.area_cs.append(cs)
-            crit = np.asarray(o["critical_pcs_idx"]).astype(np.int64)
-            edges = np.asarray(o["edges"]).reshape(-1, 2)
-            for e in range(edges.shape[0]):
-                idx2, idx1 = int(edges[e, 0]), int(edges[e, 1])
-                corr = np.asarray(o["correspondences"][e]).reshape(-1, 2)
-                src = base + cs[idx1] + crit[cs[idx1] + corr[:, 0]]
-                tgt = base + cs[idx2] + crit[cs[idx2] + corr[:, 1]]
-                pair_src.append(src)
-                pair_tgt.append(tgt)
-                e_start.append(pos)
-                e_len.append(len(src))
-                e_row.append(b * self.E_full + tri[(idx1, idx2)])
-                pos += len(src)
+            pair_src.append(base + src)
+            pair_tgt.append(base + tgt)
+            e_start.append(pos + np.concatenate([[0], np.cumsum(lens)[:-1]]) if len(lens) else np.zeros(0, dtype=np.int64))
+            e_len.append(lens)
+            e_row.append(b * self.E_full + rows)
+            pos += int(lens.sum())
             base += pts[-1].shape[0]
+        e_start = np.concatenate(e_start) if e_start else np.zeros(0, dtype=np.int64)
+        e_len = np.concatenate(e_len) if e_len else np.zeros(0, dtype=np.int64)
+        e_row = np.concatenate(e_row) if e_row else np.zeros(0, dtype=np.int64)
         self.by_area = torch.cat(pts, 0).to(dev).contiguous()
         self.by_area_T = torch.empty_like(self.by_area)
         i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32).reshape(-1)).to(dev)  # noqa: E731
         self.pair_src = i32(np.concatenate(pair_src) if pair_src else [])
         self.pair_tgt = i32(np.concatenate(pair_tgt) if pair_tgt else [])
         self.e_start, self.e_len, self.e_row = i32(e_start), i32(e_len), i32(e_row)
-        self.n_edges = len(e_start)
-        self.max_pairs = max(e_len) if e_len else 0
+        self.n_edges = int(len(e_start))
+        self.max_pairs = int(e_len.max()) if len(e_len) else 0
         self.tri_list = list(itertools.combinations(range(P), 2))
 
 
