@@ -315,7 +315,7 @@ def main():
         t_b = time.perf_counter()
         out = {k: torch.cat([outs[i][k] for i in range(n_str)]) for k in ("pred_trans", "pred_rots")}
         order = [j for pl in parts for j in pl]
-        m = object_metrics(out, [objects[j] for j in order]).to(dev)  # [B,4] per-object metric block
+        m = object_metrics(out, [objects[j] for j in order], engine=eng).to(dev)  # [B,4] per-object metric block
         if os.environ.get("PFPP_BENCH_PHASES"):
             torch.cuda.synchronize()
             print(f"[phases] runners {1e3 * (t_a - t_0):.1f} ms, loop {1e3 * (t_b - t_a):.1f} ms, metrics "

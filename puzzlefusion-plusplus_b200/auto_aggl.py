@@ -198,7 +198,7 @@ class AutoAgglomerative(_Base):
         # the reference mutates ref_part in place (auto_aggl.py:220)
         if torch.is_tensor(data_dict.get("ref_part")):
             data_dict["ref_part"].copy_(out["ref_part"].to(data_dict["ref_part"].device))
-        m = object_metrics(out, objs, e.device).cpu()
+        m = object_metrics(out, objs, e.device, engine=e).cpu()
         self.acc_list.append(m[:, 0])
         self.rmse_r_list.append(m[:, 1])
         self.rmse_t_list.append(m[:, 2])

@@ -69,10 +69,13 @@ def metrics_block(pts, pred_t, pred_r, gt_t, gt_r, valids):
     return torch.stack([acc, rmse_r, rmse_t, scd], 1)
 
 
-def object_metrics(out, objects, device=None):
-    """Metric block for the result dict of loop.run_batch and its list of input objects."""
-    device = device or torch.device("cuda", torch.cuda.current_device())
+def object_metrics(out, objects, device=None, engine=None):
+    """Metric block for the result dict of loop.run_batch and its list of input objects.  With ``engine`` the
+    fragment clouds go to the device through the engine's pinned staging buffer (the pageable copy of 7.7 MB per
+    32 objects otherwise costs more host time than the metric kernels)."""
+    device = device or (engine.device if engine is not None else torch.device("cuda", torch.cuda.current_device()))
     st = lambda k: torch.stack([o[k] for o in objects]).to(device)  # noqa: E731
-    pts = st("part_pcs") * st("part_scale").unsqueeze(-1)
+    pcs = engine.upload("metric_pcs", [o["part_pcs"] for o in objects]) if engine is not None else st("part_pcs")
+    pts = pcs * st("part_scale").unsqueeze(-1)
     return metrics_block(pts, out["pred_trans"].to(device), out["pred_rots"].to(device), st("part_trans"),
                          st("part_rots"), st("part_valids"))

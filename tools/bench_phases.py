@@ -45,7 +45,7 @@ for rep in range(5):
     t.append(sync())
     out = r.result()
     t.append(sync())
-    m = object_metrics(out, objs).to(dev)
+    m = object_metrics(out, objs, engine=eng).to(dev)
     t.append(sync())
     names = ["BatchState (H2D)", "BatchRunner init", "begin_iteration", "step 0 (eager)", "step 1 (capture+replay)",
              f"{T - 2} graph replays", "end_iteration (verify)", "result()", "object_metrics"]
