@@ -65,6 +65,8 @@ class Engine:
         self.fused_sa = True     # fused gather + 3-layer MLP + max tcgen05 kernel in bf16 mode
         self.local_tiles = 4     # 125-token tiles (5 fragments) per local-attention CTA, two per softmax group
         self._ws = {}
+        self._ws_version = 0
+        self._step_ctx = {}  # loop.StepContext cache: persistent step buffers + captured graph per batch geometry
         # The checkpoints, packed weights and synthetic/real objects are long-lived: move everything allocated so
         # far into the permanent generation so that the cyclic GC's full collections (triggered by the small host
         # objects of the agglomeration loop) do not re-traverse them -- measured: ~100 ms pauses per batch of 32
@@ -80,6 +82,7 @@ class Engine:
         if t is None or t.numel() < n or t.dtype != dtype:
             t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self._ws[name] = t
+            self._ws_version += 1  # captured CUDA graphs hold the old pointer: loop.StepContext re-captures
         return t[:n].view(*shape)
 
     def upload(self, name, host_tensors, dtype=torch.float32):

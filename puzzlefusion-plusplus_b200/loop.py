@@ -179,6 +179,49 @@ class BatchState:
         self.tri_list = list(itertools.combinations(range(P), 2))
 
 
+class StepContext:
+    """Persistent device buffers for the DDPM-step launch sequence of one batch geometry (slots, points per
+    fragment, packed fragments F, active objects, longest object) plus the CUDA graph captured over them.
+
+    A graph replays fixed addresses, so everything a step reads that changes from batch to batch (poses, noise,
+    packed-fragment tables, attention segments, the fragment clouds themselves) is copied INTO these buffers at the
+    start of an outer iteration instead of being freshly allocated.  The graph is then captured once per geometry
+    and engine and replayed for every later batch of that geometry from step 0 on -- no eager step, no capture, no
+    graph construction / destruction per batch (those cost ~3 ms per batch and leave the GPU idle whenever the host
+    stalls during them)."""
+    MAX_CACHED = 6
+
+    def __init__(self, e, slots, N, F, n_obj):
+        dev, T = e.device, e.T
+        f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+        self.x = torch.empty(slots, 7, **f32)
+        self.ref_pose = torch.empty(slots, 7, **f32)
+        self.ref_dev = torch.empty(slots, dtype=torch.uint8, device=dev)
+        self.frag_slot = torch.empty(F, **i32)
+        self.frag_step = torch.zeros(F, **i32)
+        self.loc = (torch.empty(F, **i32), torch.empty(F, **i32))
+        self.glo = (torch.empty(n_obj, **i32), torch.empty(n_obj, **i32))
+        self.noise_all = torch.empty(T, slots, 7, **f32)
+        self.x_hist = torch.empty(T, slots, 7, **f32)
+        self.step_ctr = torch.zeros(1, **i32)
+        self.part_pcs = torch.empty(slots, N, 3, **f32)
+        self.scale = torch.empty(slots, **f32)
+        self.graph = None
+        self.ws_version = -1
+
+    @staticmethod
+    def get(e, slots, N, F, n_obj, max_global):
+        key = (slots, N, F, n_obj, max_global, e.T)
+        cache = e._step_ctx
+        ctx = cache.pop(key, None)
+        if ctx is None:
+            ctx = StepContext(e, slots, N, F, n_obj)
+            while len(cache) >= StepContext.MAX_CACHED:
+                cache.pop(next(iter(cache)))  # least recently used
+        cache[key] = ctx  # most recently used last
+        return ctx
+
+
 def _seg_tensors(engine, frag_counts):
     """local (per fragment) and global (per object) attention segments over the packed tokens."""
     L, dev = engine.L, engine.device
@@ -197,8 +240,9 @@ class BatchRunner:
         begin_iteration() -> step() x T -> end_iteration()
     The T DDPM steps of an iteration share one launch sequence whose only step-dependent inputs (AdaLN
     row, scheduler coefficients, noise row, history row) are indexed by a DEVICE-side step counter; with
-    ``use_graph`` the sequence is captured once per iteration (after an eager first step that also sizes
-    the workspaces) and replayed as a CUDA graph."""
+    ``use_graph`` the sequence runs over the persistent buffers of a StepContext and is captured once per batch
+    geometry (after an eager first step that also sizes the workspaces); every later iteration / batch of the same
+    geometry replays the cached graph from its first step on."""
 
     def __init__(self, engine, objects=None, max_iters=1, threshold=0.9, noise=None, merge=True, record=None,
                  trajectory=True, state=None, verify_last=False, use_graph=True):
@@ -217,7 +261,8 @@ class BatchRunner:
         self.x = x.reshape(B * P, 7).contiguous()
         self.ref_pose = ref_pose.reshape(B * P, 7).contiguous()
         self.ref_dev = ref_mask.reshape(B * P).to(torch.uint8).contiguous()
-        self.x_hist = torch.empty(max_iters * engine.T, B * P, 7, device=dev)
+        # eager mode records the trajectory here; graph mode uses the StepContext's per-iteration history buffer
+        self.x_hist = None if self.use_graph else torch.empty(max_iters * engine.T, B * P, 7, device=dev)
         self.traj = [[] for _ in range(B)]
         self.iters = [0] * B
         self.timesteps = [int(t) for t in engine.sched.timesteps]
@@ -243,23 +288,51 @@ class BatchRunner:
             s = [b * P + p for p in range(P) if st.valid[b, p]]
             slots += s
             counts.append(len(s))
-        self.frag_slot = torch.as_tensor(np.asarray(slots, dtype=np.int32)).to(e.device)
         self.F = len(slots)
-        self.frag_step = torch.zeros(self.F, dtype=torch.int32, device=e.device)
-        self.seg_local, self.seg_global, self.max_global = _seg_tensors(e, counts)
-        self.noise_all = self.noise.iteration_noise(st.B, P, self.timesteps)
-        self.step_ctr.zero_()
+        frag_slot = torch.as_tensor(np.asarray(slots, dtype=np.int32))
+        noise_all = self.noise.iteration_noise(st.B, P, self.timesteps)
+        if self.use_graph:
+            # persistent buffers + cached graph of this batch geometry: copy this iteration's inputs in
+            max_global = int(max(counts)) * e.L
+            ctx = self.ctx = StepContext.get(e, st.B * P, st.N, self.F, len(counts), max_global)
+            ctx.frag_slot.copy_(frag_slot)
+            starts = np.concatenate([[0], np.cumsum(counts)[:-1]]) * e.L
+            ctx.loc[0].copy_(torch.arange(self.F, dtype=torch.int32) * e.L)
+            ctx.loc[1].fill_(e.L)
+            ctx.glo[0].copy_(torch.as_tensor(starts.astype(np.int32)))
+            ctx.glo[1].copy_(torch.as_tensor((np.asarray(counts) * e.L).astype(np.int32)))
+            ctx.noise_all.copy_(noise_all)
+            for name in ("x", "ref_pose", "ref_dev"):
+                cur, buf = getattr(self, name), getattr(ctx, name)
+                if cur is not buf:
+                    buf.copy_(cur)
+                    setattr(self, name, buf)
+            ctx.part_pcs.copy_(st.part_pcs)
+            ctx.scale.copy_(st.scale)
+            ctx.step_ctr.zero_()
+            self.frag_slot, self.frag_step, self.noise_all, self.step_ctr = ctx.frag_slot, ctx.frag_step, ctx.noise_all, ctx.step_ctr
+            self.seg_local, self.seg_global, self.max_global = ctx.loc, ctx.glo, max_global
+            self.pcs, self.scale_dev, self.hist = ctx.part_pcs, ctx.scale, ctx.x_hist
+            self.graph = ctx.graph if ctx.ws_version == e._ws_version else None
+        else:
+            self.ctx = None
+            self.frag_slot = frag_slot.to(e.device)
+            self.frag_step = torch.zeros(self.F, dtype=torch.int32, device=e.device)
+            self.seg_local, self.seg_global, self.max_global = _seg_tensors(e, counts)
+            self.noise_all = noise_all
+            self.step_ctr.zero_()
+            self.pcs, self.scale_dev, self.hist = st.part_pcs, st.scale, self.x_hist[self.it * e.T:]
+            self.graph = None
         self.si = 0
-        self.graph = None
         return True
 
     def _launch_step(self):
         st, e = self.st, self.e
         call("pfpp_step_broadcast", self.step_ctr.data_ptr(), self.frag_step.data_ptr(), self.F)
-        latent, xyz = e.encode(st.part_pcs, self.frag_slot, self.x, st.N)
-        eps = e.denoise_eps(self.x, st.scale, self.ref_dev, self.frag_slot, self.frag_step, latent, xyz, self.seg_local,
+        latent, xyz = e.encode(self.pcs, self.frag_slot, self.x, st.N)
+        eps = e.denoise_eps(self.x, self.scale_dev, self.ref_dev, self.frag_slot, self.frag_step, latent, xyz, self.seg_local,
                             self.seg_global, self.max_global)
-        hist = self.x_hist[self.it * e.T:]
+        hist = self.hist
         call("pfpp_ddpm_step", eps.data_ptr(), 8, self.frag_slot.data_ptr(), e.coef.data_ptr(), self.frag_step.data_ptr(),
              1, self.noise_all.data_ptr(), self.noise_all.stride(0), self.ref_dev.data_ptr(), self.ref_pose.data_ptr(),
              self.F, self.x.data_ptr(), hist.data_ptr(), hist.stride(0))
@@ -288,6 +361,8 @@ class BatchRunner:
                     g.capture_end()
             cur.wait_stream(self._cap_stream)
             self.graph = g
+            if self.ctx is not None:  # later batches of this geometry replay it from step 0 on
+                self.ctx.graph, self.ctx.ws_version = g, e._ws_version
             g.replay()
         else:
             eps = self._launch_step()
@@ -304,7 +379,7 @@ class BatchRunner:
             self.iters[b] += 1
         x_host = self.x.cpu().reshape(B, P, 7)  # the one D2H read of this outer iteration
         if self.trajectory:
-            xh = self.x_hist[self.it * T:(self.it + 1) * T].cpu().reshape(T, B, P, 7)
+            xh = self.hist[:T].cpu().reshape(T, B, P, 7)
             for b in self.active:
                 self.traj[b].append(compose_params_steps(xh[:, b], st.pivot[b], st.init_pose[b]))
         last = self.it + 1 == self.max_iters
