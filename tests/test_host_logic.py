@@ -152,3 +152,56 @@ def test_sharding_and_metric_gather_gloo_world2():
         assert allm[:, 1].tolist() == [20.0, 3.0, 11.0, 8.0, 15.0, 2.0, 9.0, 20.0]
     loads = [sum([20, 3, 11, 8, 15, 2, 9, 20][i] for i in r[1]) for r in res]
     assert abs(loads[0] - loads[1]) <= 4  # balanced by fragment count
+
+
+def test_compose_params_batch_matches_per_object():
+    """the batched result composition (one call per batch) == compose_params per object, with and without
+    accumulated init poses, padded rows zero."""
+    from puzzlefusion_plusplus_b200.pose_utils import affine, compose_params, compose_params_batch, quat_to_matrix
+    g = torch.Generator().manual_seed(7)
+    B, P = 3, 20
+    x = torch.randn(B, P, 7, generator=g)
+    num_parts = [5, 20, 9]
+    pivots, inits = [], []
+    for b, n in enumerate(num_parts):
+        pv = [int(v) for v in torch.randint(0, n, (n,), generator=g)]
+        ip = []
+        for i in range(n):
+            if (i + b) % 3 == 0:
+                q = torch.randn(4, generator=g)
+                ip.append(affine(quat_to_matrix(q[None])[0], torch.randn(3, generator=g)))
+            else:
+                ip.append(None)
+        pivots.append(pv)
+        inits.append(ip)
+    tb, qb = compose_params_batch(x, pivots, inits, num_parts)
+    for b, n in enumerate(num_parts):
+        t, q = compose_params(x[b], pivots[b], inits[b])
+        assert torch.allclose(tb[b, :n], t, atol=1e-6) and torch.allclose(qb[b, :n], q, atol=1e-6)
+        assert float(tb[b, n:].abs().sum()) == 0.0 and float(qb[b, n:].abs().sum()) == 0.0
+
+
+def test_batch_state_matching_tables_cached_per_object():
+    """BatchState builds the per-object correspondence tables once (kept on the object dict) and offsets them per
+    batch position: a second batch containing the same objects in another order gets consistent tables."""
+    from puzzlefusion_plusplus_b200 import synthetic
+    from puzzlefusion_plusplus_b200.loop import BatchState
+
+    class E:  # minimal engine stand-in (CPU): BatchState only needs the device and the slot count
+        device = torch.device("cpu")
+        P = 20
+    o1, o2 = synthetic.make_object(61, num_parts=6), synthetic.make_object(62, num_parts=9)
+    a = BatchState(E, [o1, o2])
+    assert "_pfpp_matching" in o1 and "_pfpp_matching" in o2
+    b = BatchState(E, [o2, o1])  # cached tables, swapped order
+    fresh1, fresh2 = synthetic.make_object(61, num_parts=6), synthetic.make_object(62, num_parts=9)
+    c = BatchState(E, [fresh2, fresh1])  # no cache
+    for name in ("pair_src", "pair_tgt", "e_start", "e_len", "e_row"):
+        assert torch.equal(getattr(b, name), getattr(c, name)), name
+    assert a.n_edges == b.n_edges == c.n_edges and a.max_pairs == c.max_pairs
+    # the swapped batch addresses the same points, shifted by the other object's by-area cloud
+    n1 = o1["part_pcs_by_area"].shape[0]
+    e1 = int((a.e_row < a.E_full).sum())  # edges of o1 (first object of batch a)
+    n_pairs1 = int(a.e_len[:e1].sum())
+    assert torch.equal(a.pair_src[:n_pairs1] + o2["part_pcs_by_area"].shape[0], b.pair_src[-n_pairs1:])
+    assert n1 > 0
