@@ -424,19 +424,26 @@ extern "C" int pfpp_group_max(const void* in, long long G, int ns, int C, int ld
 // (first minimum), output z + (e - z).  Codebook (64 KB) + |e|^2 staged in shared memory; all threads of a
 // warp read the same code row (smem broadcast).  A broadcast LDS.128 returns 512 B per warp, so the scan is
 // bound by shared-memory return bandwidth unless every code row is reused: each thread scans for VQ_R chunks
-// at once (the arithmetic per (chunk, code) pair is unchanged).
+// at once (the arithmetic per (chunk, code) pair is unchanged).  The VQ_WARPS warps of a CTA work on the SAME
+// 32 x VQ_R chunks and split the code range (warp w scans codes [w, w+1) * n_codes / VQ_WARPS in increasing
+// order); the partial (distance, code) winners are merged in warp order with a strict <, which keeps the
+// first-minimum rule.  This gives 4x the warps of a one-warp-per-chunk-set layout at the same shared-memory traffic.
 // ---------------------------------------------------------------------------------------------
 #define VQ_DIM 16
-#define VQ_THREADS 64
+#define VQ_WARPS 4
+#define VQ_THREADS (32 * VQ_WARPS)
 #define VQ_R 4
+#define VQ_CHUNKS_PER_CTA (32 * VQ_R)
 
 template <typename InT>
 __global__ void __launch_bounds__(VQ_THREADS)
     vq_kernel(const InT* __restrict__ z, long long n_chunks, const float* __restrict__ codebook, int n_codes,
               float* __restrict__ out, int* __restrict__ codes) {
   extern __shared__ float sm[];
-  float* cb = sm;                      // [n_codes][16]
-  float* cn = sm + (size_t)n_codes * VQ_DIM;  // [n_codes]
+  float* cb = sm;                                   // [n_codes][16]
+  float* cn = sm + (size_t)n_codes * VQ_DIM;        // [n_codes]
+  float* pd = cn + n_codes;                         // [VQ_WARPS][VQ_CHUNKS_PER_CTA] partial best distance
+  int* pi = reinterpret_cast<int*>(pd + VQ_WARPS * VQ_CHUNKS_PER_CTA);  // partial best code
   for (int i = threadIdx.x; i < n_codes * VQ_DIM / 4; i += VQ_THREADS)
     reinterpret_cast<float4*>(cb)[i] = reinterpret_cast<const float4*>(codebook)[i];
   __syncthreads();
@@ -446,21 +453,23 @@ __global__ void __launch_bounds__(VQ_THREADS)
     cn[c] = s;
   }
   __syncthreads();
-  const long long T = (long long)gridDim.x * VQ_THREADS;
-  for (long long i0 = (long long)blockIdx.x * VQ_THREADS + threadIdx.x; i0 < n_chunks; i0 += T * VQ_R) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c_lo = (int)((long long)n_codes * warp / VQ_WARPS), c_hi = (int)((long long)n_codes * (warp + 1) / VQ_WARPS);
+  for (long long base = (long long)blockIdx.x * VQ_CHUNKS_PER_CTA; base < n_chunks;
+       base += (long long)gridDim.x * VQ_CHUNKS_PER_CTA) {
     float zv[VQ_R][VQ_DIM], zz[VQ_R], best[VQ_R];
     int bi[VQ_R];
 #pragma unroll
     for (int r = 0; r < VQ_R; ++r) {
-      const long long i = i0 + r * T;
-      zz[r] = 0.f, best[r] = INFINITY, bi[r] = 0;
+      const long long i = base + r * 32 + lane;
+      zz[r] = 0.f, best[r] = INFINITY, bi[r] = c_lo;
 #pragma unroll
       for (int d = 0; d < VQ_DIM; ++d) {
         zv[r][d] = i < n_chunks ? (float)z[i * VQ_DIM + d] : 0.f;
         zz[r] += zv[r][d] * zv[r][d];
       }
     }
-    for (int c = 0; c < n_codes; ++c) {
+    for (int c = c_lo; c < c_hi; ++c) {
       const float4* e = reinterpret_cast<const float4*>(cb + c * VQ_DIM);
       const float4 e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
       const float en = cn[c];
@@ -475,13 +484,33 @@ __global__ void __launch_bounds__(VQ_THREADS)
         if (dist < best[r]) best[r] = dist, bi[r] = c;
       }
     }
+    __syncthreads();  // the partial tables of the previous round have been consumed
 #pragma unroll
     for (int r = 0; r < VQ_R; ++r) {
-      const long long i = i0 + r * T;
-      if (i < n_chunks) {
-        if (codes) codes[i] = bi[r];
+      pd[warp * VQ_CHUNKS_PER_CTA + r * 32 + lane] = best[r];
+      pi[warp * VQ_CHUNKS_PER_CTA + r * 32 + lane] = bi[r];
+    }
+    __syncthreads();
+    // warp w finalises the chunks r == w: merge the partial winners in code order (strict <: first minimum)
+    {
+      const int r = warp;
+      const int slot = r * 32 + lane;
+      const long long i = base + slot;
+      float bd = pd[slot];
+      int bc = pi[slot];
 #pragma unroll
-        for (int d = 0; d < VQ_DIM; ++d) out[i * VQ_DIM + d] = fadd(zv[r][d], fsub(cb[bi[r] * VQ_DIM + d], zv[r][d]));
+      for (int w2 = 1; w2 < VQ_WARPS; ++w2) {
+        const float d2 = pd[w2 * VQ_CHUNKS_PER_CTA + slot];
+        if (d2 < bd) bd = d2, bc = pi[w2 * VQ_CHUNKS_PER_CTA + slot];
+      }
+      if (i < n_chunks) {
+        if (codes) codes[i] = bc;
+        // z is re-read here (indexing zv[] with the runtime warp id would push the whole array to local memory)
+#pragma unroll
+        for (int d = 0; d < VQ_DIM; ++d) {
+          const float zd = (float)z[i * VQ_DIM + d];
+          out[i * VQ_DIM + d] = fadd(zd, fsub(cb[bc * VQ_DIM + d], zd));
+        }
       }
     }
   }
@@ -491,9 +520,10 @@ extern "C" int pfpp_vq(const void* z, int z_is_bf16, long long n_chunks, const f
                        float* out, int* codes, cudaStream_t stream) {
   PFPP_CHECK_ARG(z && codebook && out && n_codes > 0);
   if (n_chunks == 0) return PFPP_OK;
-  size_t smem = (size_t)n_codes * (VQ_DIM + 1) * sizeof(float);
+  static_assert(VQ_R == VQ_WARPS, "warp w finalises chunk set w");
+  size_t smem = (size_t)n_codes * (VQ_DIM + 1) * sizeof(float) + (size_t)VQ_WARPS * VQ_CHUNKS_PER_CTA * 8;
   if (smem > 200 * 1024) return PFPP_EUNSUPPORTED;
-  int grid = (int)((n_chunks + VQ_THREADS * VQ_R - 1) / (VQ_THREADS * VQ_R));
+  int grid = (int)((n_chunks + VQ_CHUNKS_PER_CTA - 1) / VQ_CHUNKS_PER_CTA);
   if (grid > 148 * 3) grid = 148 * 3;
   if (z_is_bf16) {
     PFPP_ENSURE_SMEM(vq_kernel<__nv_bfloat16>, smem);
