@@ -314,6 +314,7 @@ class BatchRunner:
             self.seg_local, self.seg_global, self.max_global = ctx.loc, ctx.glo, max_global
             self.pcs, self.scale_dev, self.hist = ctx.part_pcs, ctx.scale, ctx.x_hist
             self.graph = ctx.graph if ctx.ws_version == e._ws_version else None
+            self.graph_launches = getattr(ctx, "graph_launches", 0)
         else:
             self.ctx = None
             self.frag_slot = frag_slot.to(e.device)
@@ -345,6 +346,7 @@ class BatchRunner:
         e = self.e
         if self.graph is not None:
             self.graph.replay()
+            _lib.launch_count += self.graph_launches  # kernels of the replayed graph (bench.py's gpu_launches)
         elif self.use_graph and self.si == 1 and e.T > 2:
             # capture on a private side stream (no host synchronisation, no allocator flush), replay on the
             # runner's stream
@@ -353,6 +355,7 @@ class BatchRunner:
             if self._cap_stream is None:
                 self._cap_stream = torch.cuda.Stream(device=e.device)
             self._cap_stream.wait_stream(cur)
+            n0 = _lib.launch_count
             with torch.cuda.stream(self._cap_stream):
                 g.capture_begin()
                 try:
@@ -360,10 +363,12 @@ class BatchRunner:
                 finally:
                     g.capture_end()
             cur.wait_stream(self._cap_stream)
-            self.graph = g
+            self.graph, self.graph_launches = g, _lib.launch_count - n0  # (the captured calls are counted at replay)
+            _lib.launch_count = n0
             if self.ctx is not None:  # later batches of this geometry replay it from step 0 on
-                self.ctx.graph, self.ctx.ws_version = g, e._ws_version
+                self.ctx.graph, self.ctx.ws_version, self.ctx.graph_launches = g, e._ws_version, self.graph_launches
             g.replay()
+            _lib.launch_count += self.graph_launches
         else:
             eps = self._launch_step()
             if self.record is not None:
