@@ -223,6 +223,40 @@ def golden_loop_full(seed=321, num_parts=8, steps=4, max_iters=4):
             "meta": torch.tensor([seed, num_parts, steps, max_iters])}
 
 
+DATASET_CASES = ((701, 3, 48, 200), (702, 5, 48, 300))  # (seed, num_parts, points per part, by-area points)
+DATASET_NP_SEED = 1234
+
+
+def dataset_cfg(matching_dir):
+    """The fields of the composed config that the reference dataset reads (dataset.py:24-31, 229)."""
+    return _shims.AttrDict.wrap({"data": {"max_num_part": 20, "matching_data_path": matching_dir},
+                                 "model": {"multiple_ref_parts": False}})
+
+
+def golden_dataset():
+    """The reference's OWN GeometryLatentDataset (test mode) on two tiny synthetic objects written in the
+    reference's on-disk formats; NumPy's global generator seeded once before the samples are drawn in order."""
+    import tempfile
+    _shims.install()
+    from puzzlefusion_plusplus.denoiser.dataset.dataset import GeometryLatentDataset as RefDataset
+    from puzzlefusion_plusplus_b200 import dataset as pd
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        pc_dir, m_dir = os.path.join(tmp, "pc_data", "val"), os.path.join(tmp, "matching_data")
+        for seed, n, pts, area in DATASET_CASES:
+            pd.save_reference_format(synthetic.make_raw_object(seed, num_parts=n, n_points=pts, n_by_area=area), pc_dir, m_dir)
+        ds = RefDataset(dataset_cfg(m_dir), pc_dir, -1, "test")
+        np.random.seed(DATASET_NP_SEED)
+        for i in range(len(ds)):
+            smp = ds[i]
+            for k in ("part_pcs", "part_scale", "part_trans", "part_rots", "part_pcs_by_area", "init_pose_r", "init_pose_t",
+                      "part_pcs_gt"):
+                out[f"{i}.{k}"] = torch.as_tensor(np.asarray(smp[k]))
+            out[f"{i}.data_id"] = torch.tensor(smp["data_id"])
+            out[f"{i}.n_corr"] = torch.tensor([len(smp["correspondences"])])
+    return out
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     model = build_reference_model()
@@ -234,6 +268,9 @@ def main():
     out = _np(golden_loop_config1())
     np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_loop_config1.npz"), **out)
     print("loop_config1", {k: v.shape for k, v in out.items()})
+    out = _np(golden_dataset())
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_dataset.npz"), **out)
+    print("dataset", {k: v.shape for k, v in out.items()})
     for seed in (321, 323):
         out = _np(golden_loop_full(seed))
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"ref_loop_full_{seed}.npz"), **out)

@@ -179,7 +179,10 @@ class AutoAgglomerative(_Base):
             o = {}
             for k, v in data_dict.items():
                 if k == "correspondences":
-                    o[k] = [c[b] if c.dim() == 3 else c for c in v]
+                    if len(v) and isinstance(v[0], (list, tuple)):  # dataset.collate with B > 1: one list per object
+                        o[k] = list(v[b])
+                    else:  # the reference's B = 1 layout: list of [1, K_e, 2]
+                        o[k] = [c[b] if c.dim() == 3 else c for c in v]
                 elif torch.is_tensor(v):
                     o[k] = v[b].detach().cpu()
                 else:

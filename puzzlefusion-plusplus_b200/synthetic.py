@@ -30,9 +30,36 @@ def _quat_wxyz(rot_mat):
     return q[[3, 0, 1, 2]]
 
 
-def make_object(seed, num_parts=20, n_points=1000, max_parts=MAX_PARTS, n_by_area=N_BY_AREA, data_id=None):
-    """Returns a dict of torch tensors (no batch dim) + python lists; see module docstring."""
-    rng = np.random.RandomState(seed)
+def make_raw_object(seed, num_parts=20, n_points=1000, max_parts=MAX_PARTS, n_by_area=N_BY_AREA, data_id=None, _rng=None):
+    """The object BEFORE the dataset transform, in the layout of the reference's on-disk files:
+    ``pc`` = the fields of pc_data/{split}/{id:05}.npz, ``matching`` = the fields of matching_data/{id}.npz.
+    ``dataset.save_reference_format`` writes them to disk; ``dataset.GeometryLatentDataset`` reads them back."""
+    rng = _rng if _rng is not None else np.random.RandomState(seed)
+    g = _generate(rng, num_parts, n_points, max_parts, n_by_area)
+    valids = np.zeros(max_parts, dtype=np.float32)
+    valids[:num_parts] = 1
+    ref = np.zeros(max_parts, dtype=bool)
+    ref[0] = True
+    n_pcs_pad = np.zeros(max_parts, dtype=np.int64)
+    n_pcs_pad[:num_parts] = g["n_pcs"]
+    graph = np.zeros((max_parts, max_parts), dtype=bool)
+    for (j, i) in g["edges"]:
+        graph[i, j] = graph[j, i] = True
+    corr = np.empty(len(g["corr"]), dtype=object)
+    for k, c in enumerate(g["corr"]):
+        corr[k] = c
+    did = seed if data_id is None else data_id
+    return {
+        "pc": {"data_id": did, "part_valids": valids, "num_parts": num_parts, "mesh_file_path": "synthetic/ellipsoid_%d" % seed,
+               "graph": graph, "category": "synthetic", "part_pcs_gt": g["part_gt"].astype(np.float32), "ref_part": ref},
+        "matching": {"edges": np.asarray(g["edges"], dtype=np.int64).reshape(-1, 2), "correspondence": corr,
+                     "gt_pcs": g["gt_pcs"].astype(np.float32), "critical_pcs_idx": g["critical_idx"], "n_pcs": n_pcs_pad,
+                     "n_critical_pcs": g["n_critical"]},
+    }
+
+
+def _generate(rng, num_parts, n_points, max_parts, n_by_area):
+    """Ellipsoid surface -> Voronoi fragments, area-sampled cloud, critical points, edges, correspondences."""
     radii = rng.uniform(0.3, 1.0, size=3)
     pool_n = max(60000, num_parts * n_points * 3)
     pool = rng.normal(size=(pool_n, 3))
@@ -88,6 +115,16 @@ def make_object(seed, num_parts=20, n_points=1000, max_parts=MAX_PARTS, n_by_are
                 edges.append((j, i))
                 corr.append(np.stack([mutual, nab[mutual]], 1).astype(np.int64))
 
+    return {"part_gt": part_gt, "gt_pcs": gt_pcs, "n_pcs": n_pcs, "starts": starts, "critical_idx": critical_idx,
+            "n_critical": n_critical, "edges": edges, "corr": corr}
+
+
+def make_object(seed, num_parts=20, n_points=1000, max_parts=MAX_PARTS, n_by_area=N_BY_AREA, data_id=None):
+    """Returns a dict of torch tensors (no batch dim) + python lists; see module docstring."""
+    rng = np.random.RandomState(seed)
+    g = _generate(rng, num_parts, n_points, max_parts, n_by_area)
+    part_gt, gt_pcs, n_pcs, starts = g["part_gt"], g["gt_pcs"], g["n_pcs"], g["starts"]
+    critical_idx, n_critical, edges, corr = g["critical_idx"], g["n_critical"], g["edges"], g["corr"]
     # ---- dataset transform (denoiser/dataset/dataset.py:163-221) ----
     g_rot = R.random(random_state=rng).as_matrix()
     pcs = (g_rot @ part_gt.reshape(-1, 3).T).T.reshape(num_parts, n_points, 3)

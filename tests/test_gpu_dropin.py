@@ -84,3 +84,25 @@ def test_test_step_runs_like_the_reference(ckpt, tmp_path, precision):
     from puzzlefusion_plusplus_b200.loop import GlobalTorchNoise, run_batch
     res = run_batch(m2.engine, objs, max_iters=1, noise=GlobalTorchNoise(m2.engine.device))
     assert torch.isfinite(res["x"][0, :6]).all() and torch.isfinite(res["x"][1, :11]).all()
+
+
+def test_reference_files_to_test_step(ckpt, tmp_path):
+    """the whole data path: two objects written in the reference's on-disk formats -> GeometryLatentDataset ->
+    DataLoader (collate, batch of 2) -> AutoAgglomerative.test_step -> per-object metrics and result files."""
+    from puzzlefusion_plusplus_b200 import dataset as pd
+    pc_dir, m_dir = str(tmp_path / "pc_data" / "val"), str(tmp_path / "matching_data")
+    for seed, n in ((811, 6), (812, 9)):
+        pd.save_reference_format(synthetic.make_raw_object(seed, num_parts=n), pc_dir, m_dir)
+    cfg = {"data": {"max_num_part": 20, "matching_data_path": m_dir, "data_val_dir": pc_dir, "val_batch_size": 2,
+                    "num_workers": 0, "overfit": -1}}
+    np.random.seed(5)
+    torch.manual_seed(5)
+    m = _model(ckpt, tmp_path, "bf16", max_iters=2)
+    for i, batch in enumerate(pd.build_test_dataloader(cfg)):
+        assert batch["part_pcs"].shape == (2, 20, 1000, 3)
+        m.test_step(batch, i)
+    assert len(m.acc_list) == 1 and m.acc_list[0].shape == (2,)  # one entry per test_step call, one value per object
+    res = tmp_path / "output" / "denoiser" / "t" / "inference" / "results"
+    assert sorted(os.listdir(res)) == ["811", "812"]
+    tot = m.on_test_epoch_end()
+    assert all(torch.isfinite(t) for t in tot)
