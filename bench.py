@@ -23,7 +23,6 @@ no data-path collective; one NCCL all_gather of the per-object metric block ends
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

@@ -6,7 +6,6 @@ auto_aggl.py:291-317: posing runs in pfpp_pose_apply (raw quaternion, as transfo
 Chamfer terms in pfpp_nn_sqdist; the [B,P]-sized reductions are torch glue.  The [B,4] block
 (part_acc, rmse_r, rmse_t, shape_cd) is what the ranks all-gather at the end of a step.
 """
-import math
 
 import torch
 
