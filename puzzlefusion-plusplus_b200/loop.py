@@ -211,7 +211,9 @@ class StepContext:
 
     @staticmethod
     def get(e, slots, N, F, n_obj, max_global):
-        key = (slots, N, F, n_obj, max_global, e.T)
+        # the launch sequence also depends on the engine's kernel-selection switches: part of the key, so that a
+        # graph captured under other settings is never replayed
+        key = (slots, N, F, n_obj, max_global, e.T, e.fused_sa, e.tc_attention, e.local_tiles)
         cache = e._step_ctx
         ctx = cache.pop(key, None)
         if ctx is None:
