@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- objects/sec of the denoise-and-verify hot path (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32|tc32]
+                    [--workload config3|config2|config5]
 
-A "step" is one pass of the hot path over one batch of synthetic objects of BASELINE config 2:
-20 fragments x 1000 points, 100 DDPM steps (encoder + denoiser + DDPM update each), then one
-verifier pass (pose by-area clouds, edge histograms, verifier transformer, accept decisions).
-``--batch`` objects are advanced in lock-step per GPU (default 32); objects/sec = batch*K*N / time.
+A "step" is one pass of the hot path over one batch of synthetic objects.  Workloads (SURVEY 8d / BASELINE.json):
+
+  config3 (default, the BASELINE metric: "full auto-aggl loop"): 32 DISTINCT objects per GPU with
+          num_parts ~ U{8..20}, 1000 points per fragment, 100 DDPM steps per outer iteration, max_iters = 6 outer
+          denoise -> verify -> merge iterations with merges and early exits on (auto_aggl.py:136-289), a new noise
+          seed for every object of every step.  With N GPUs this is BASELINE config 4: 32*N objects dealt to the ranks
+          by the package's own `sharding.shard_objects`, metrics gathered with `sharding.gather_metrics`.
+  config2: 32 objects x 20 fragments, one denoise pass (100 DDPM steps) + one verifier pass, no merge; also measured
+          as the `secondary` key of the default run.
+  config5: 64 fragments x 2000 points, 250 DDPM steps, 8 objects in flight.
 
   value : device-timed (CUDA events on the launch stream), inputs already resident in HBM
-  e2e   : the same batch through the public call (run_batch on HOST tensors): H2D of every input
-          and D2H of the predicted poses inside the timed region
-  roofline : the tensor-core kernel with the largest share of the DDPM step (fused set abstraction, GEMM or
-          attention): algorithmic FLOPs / CUDA-event time of its launches against MEASURED_PEAKS.json
-          (sustained bf16), measured in an eager single-stream probe pass inside bench.py; `kernels` lists every
-          probed entry point (per-DDPM-step time, share, TFLOP/s)
+  e2e   : the same batches through the public call on HOST tensors: H2D of every input and D2H of the predicted
+          poses / verifier logits inside the timed region
+  roofline : the tensor-core kernel with the largest share of the DDPM step, per set-abstraction level: algorithmic
+          FLOPs / CUDA-event time of its launches against MEASURED_PEAKS.json (sustained bf16), measured in an eager
+          single-stream probe pass inside bench.py; `kernels` lists every probed entry point
   cpu_baseline : the oracle (CPU port of the reference path) on the host cores, bounded sample
 
-Multi-GPU (torchrun, one rank per GPU): objects are independent, so ranks run disjoint batches with
-no data-path collective; one NCCL all_gather of the per-object metric block ends every step.
+Multi-GPU (torchrun, one rank per GPU): objects are independent, so ranks run disjoint batches with no data-path
+collective; one NCCL all_gather of the per-object metric block ends every step.
 """
 import argparse
 import json
@@ -36,51 +42,90 @@ sys.path.insert(0, ROOT)
 METRIC = "objects/sec (full auto-aggl loop, 20 frags, 100 DDPM steps) @1/2/4/8 B200"
 UNIT = "objects/s"
 
+# frags: int = every object has that many fragments; (lo, hi) = num_parts ~ U{lo..hi}.  accept_bias: the synthetic
+# verifier's output bias (synthetic.make_verifier_state): -1.0 spreads the outer-iteration counts (measured: mean 3.1
+# iterations per object, 1 in 6 objects runs all 6) where the goldens' 3.1 lets 31 of 32 objects leave after 2.
+WORKLOADS = {
+    "config3": dict(frags=(8, 20), points=1000, ddpm_steps=100, max_iters=6, merge=True, verify_last=False, batch=32,
+                    accept_bias=-1.0, slots=2),
+    "config2": dict(frags=20, points=1000, ddpm_steps=100, max_iters=1, merge=False, verify_last=True, batch=32,
+                    accept_bias=3.1, slots=1),
+    "config5": dict(frags=64, points=2000, ddpm_steps=250, max_iters=1, merge=False, verify_last=True, batch=8,
+                    accept_bias=3.1, slots=1),
+}
+STATS_FILE = os.path.join(ROOT, "profiles", "r2_config3_workload_stats.json")
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=32, help="objects in flight per GPU")
-    ap.add_argument("--frags", type=int, default=20)
-    ap.add_argument("--points", type=int, default=1000)
-    ap.add_argument("--ddpm-steps", type=int, default=100)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tc32"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="objects in flight per GPU and slot")
+    ap.add_argument("--frags", type=int, default=None)
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--ddpm-steps", type=int, default=None)
+    ap.add_argument("--max-iters", type=int, default=None)
+    ap.add_argument("--slots", type=int, default=None,
+                    help="batches in flight per GPU (one Engine + CUDA stream each, loop.run_pipelined): the late, "
+                         "nearly empty outer iterations of one batch run under the full early iterations of the next")
     ap.add_argument("--cpu-sample-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 measurement of the default run")
     ap.add_argument("--chunk", type=int, default=32)
-    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll NVML during the timed region")
     ap.add_argument("--no-graph", action="store_true", help="launch every DDPM step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--streams", type=int, default=1,
-                    help="the batch is split over this many CUDA streams (interleaved by one host thread) so that the "
-                         "latency-bound geometry kernels of one half overlap the tensor-core kernels of the other")
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = dict(WORKLOADS[a.workload])
+    for k in ("batch", "frags", "points", "ddpm_steps", "max_iters", "slots"):
+        v = getattr(a, k)
+        if v is not None:
+            w[k] = v
+    a.w = w
+    return a
 
 
-def workload_name(a):
-    tag = "config2" if (a.frags, a.points, a.ddpm_steps) == (20, 1000, 100) else (
-        "config5" if (a.frags, a.points, a.ddpm_steps) == (64, 2000, 250) else "custom")
-    return (f"{tag}: {a.frags} frags x {a.points} pts, {a.ddpm_steps} DDPM steps, 1 denoise pass + 1 verifier pass; "
-            f"{a.batch} objects in flight per GPU")
+def workload_name(a, w=None, tag=None):
+    w = w or a.w
+    tag = tag or (a.workload if all(getattr(a, k) is None for k in ("frags", "points", "ddpm_steps", "max_iters")) else "custom")
+    fr = f"{w['frags']} frags" if isinstance(w["frags"], int) else f"num_parts ~ U{{{w['frags'][0]}..{w['frags'][1]}}}"
+    loop = (f"max_iters {w['max_iters']} (denoise -> verify -> merge, early exits)" if w["merge"] else
+            "1 denoise pass + 1 verifier pass")
+    return f"{tag}: {fr} x {w['points']} pts, {w['ddpm_steps']} DDPM steps, {loop}; {w['batch']} distinct objects per GPU per step"
+
+
+def object_parts(w, total, seed=123):
+    """num_parts of the `total` objects of the global batch (same on every rank)"""
+    if isinstance(w["frags"], int):
+        return [w["frags"]] * total
+    lo, hi = w["frags"]
+    return np.random.RandomState(seed).randint(lo, hi + 1, size=total).tolist()
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_objects_per_sec(a, sample_steps):
-    """Times `sample_steps` DDPM steps (encoder + denoiser + scheduler) and one verify pass of ONE
-    config-2 object with the oracle on all host cores; extrapolates to ddpm_steps per object."""
+def cpu_objects_per_sec(a, sample_steps, stats=None):
+    """Times `sample_steps` DDPM steps (encoder + denoiser + scheduler) and one verify pass of ONE object with the
+    oracle on all host cores and extrapolates to the workload: per object,
+        T * t_step * (fragment-iterations per object / fragments of the sample object) + iterations * t_verify
+    where a fragment-iteration is one valid fragment taking part in one outer iteration (the CPU cost of a DDPM step
+    is linear in the fragment count: the encoder is per fragment, attention is 4 % of the FLOPs).  The merge stage's
+    CPU time is not counted (in the CPU arm's favour)."""
     from oracle import denoiser as od
     from oracle import encoder as oe
     from oracle import verifier as ov
     from puzzlefusion_plusplus_b200 import synthetic
     torch.set_num_threads(os.cpu_count())
-    P = max(20, a.frags)
-    ck = synthetic.make_checkpoints(0, max_parts=P)
-    obj = synthetic.make_object(1000, num_parts=a.frags, n_points=a.points, max_parts=P)
-    sched = od.make_scheduler(a.ddpm_steps)
+    w = a.w
+    n_sample = w["frags"] if isinstance(w["frags"], int) else (w["frags"][0] + w["frags"][1]) // 2
+    P = max(20, n_sample)
+    ck = synthetic.make_checkpoints(0, max_parts=P, accept_bias=w["accept_bias"])
+    obj = synthetic.make_object(1000, num_parts=n_sample, n_points=w["points"], max_parts=P)
+    sched = od.make_scheduler(w["ddpm_steps"])
     g = torch.Generator().manual_seed(0)
     x = torch.randn(P, 7, generator=g)
     t0 = time.perf_counter()
@@ -92,14 +137,27 @@ def cpu_objects_per_sec(a, sample_steps):
             x = sched.step(eps, t, x, noise=torch.randn(P, 7, generator=g)).prev_sample
         t_step = (time.perf_counter() - t0) / sample_steps
         t1 = time.perf_counter()
-        pts = ov.final_pose_pts_dynamic(obj["part_pcs_by_area"], obj["n_pcs"], x[:, :3], x[:, 3:], a.frags,
-                                        list(range(a.frags)))
+        pts = ov.final_pose_pts_dynamic(obj["part_pcs_by_area"], obj["n_pcs"], x[:, :3], x[:, 3:], n_sample,
+                                        list(range(n_sample)))
         feats, eidx = ov.edge_features(pts, obj["n_pcs"], obj["n_critical_pcs"], obj["critical_pcs_idx"], obj["edges"],
                                        obj["correspondences"], P)
-        ov.verifier_forward(ck["verifier"], feats[None], eidx[None], ov.edge_mask(a.frags, P)[None])
+        ov.verifier_forward(ck["verifier"], feats[None], eidx[None], ov.edge_mask(n_sample, P)[None])
         t_verify = time.perf_counter() - t1
-    per_object = a.ddpm_steps * t_step + t_verify
-    return 1.0 / per_object, t_step, t_verify
+    if stats is None:
+        stats = {"iterations_per_object": 1.0, "fragment_iterations_per_object": float(n_sample)}
+        if w["merge"]:
+            try:
+                stats = json.load(open(STATS_FILE))
+            except Exception:
+                stats = {"iterations_per_object": 2.0, "fragment_iterations_per_object": 2.0 * n_sample,
+                         "note": "no committed workload statistics: the two outer iterations every object runs at least"}
+    per_object = (w["ddpm_steps"] * t_step * stats["fragment_iterations_per_object"] / n_sample
+                  + stats["iterations_per_object"] * t_verify)
+    sample = (f"{sample_steps} of {w['ddpm_steps']} DDPM steps + 1 verifier pass of one {n_sample}-fragment object "
+              f"({t_step * 1e3:.0f} ms/DDPM step, {t_verify * 1e3:.0f} ms/verify), extrapolated to "
+              f"{stats['iterations_per_object']:.2f} outer iterations / {stats['fragment_iterations_per_object']:.1f} "
+              f"fragment-iterations per object (workload statistics of the GPU arm); merge stage not counted")
+    return 1.0 / per_object, sample
 
 
 def run_reference(a, rank):
@@ -110,12 +168,10 @@ def run_reference(a, rank):
         cpu_objects_per_sec(a, 1)
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        v, t_step, t_verify = cpu_objects_per_sec(a, a.cpu_sample_steps)
+        v, sample = cpu_objects_per_sec(a, a.cpu_sample_steps)
         vals.append(v)
     ms = (time.perf_counter() - t0) * 1e3 / max(a.steps, 1)
     v = float(np.median(vals))
-    sample = (f"{a.cpu_sample_steps} of {a.ddpm_steps} DDPM steps + 1 verifier pass of one object, extrapolated to "
-              f"{a.ddpm_steps} steps; {t_step * 1e3:.0f} ms/DDPM step, {t_verify * 1e3:.0f} ms/verify")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -243,7 +299,8 @@ class KernelProbe:
                 e0.record()
                 probe.orig(name, *args)
                 e1.record()
-                r = probe.rec.setdefault(name, {"events": [], "flops": 0.0})
+                key = f"{name}[level {args[0]}]" if name == "pfpp_sa_fused" else name
+                r = probe.rec.setdefault(key, {"events": [], "flops": 0.0})
                 r["events"].append((e0, e1))
                 r["flops"] += algorithmic_flops(name, args)
             else:
@@ -263,6 +320,66 @@ class KernelProbe:
         return out
 
 
+class Arm:
+    """One measured workload on this rank: engines / streams per slot, this rank's objects, timed legs."""
+
+    def __init__(self, a, w, rank, world, local, tag):
+        from puzzlefusion_plusplus_b200 import sharding, synthetic
+        from puzzlefusion_plusplus_b200.engine import Engine
+        self.a, self.w, self.rank, self.world, self.tag = a, w, rank, world, tag
+        self.dev = dev = f"cuda:{local}"
+        P = self.P = max(20, w["frags"] if isinstance(w["frags"], int) else w["frags"][1])
+        self.ck = synthetic.make_checkpoints(0, max_parts=P, accept_bias=w["accept_bias"])
+        self.n_slots = max(1, w["slots"])
+        mk = lambda: Engine(self.ck, num_inference_steps=w["ddpm_steps"], precision=a.precision, device=dev,  # noqa: E731
+                            chunk_frags=a.chunk, max_parts=P, freeze_gc=True)
+        self.engines = [mk() for _ in range(self.n_slots)]
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.n_slots)]
+        # the global batch of world*batch distinct objects, dealt by the package's sharding (serpentine by fragment count)
+        total = w["batch"] * world
+        parts = object_parts(w, total)
+        self.mine = sharding.shard_objects(parts, rank, world)
+        self.total = total
+        self.objects = [synthetic.make_object(2000 + i, num_parts=parts[i], n_points=w["points"], max_parts=P) for i in self.mine]
+        self.frag_iters, self.obj_iters, self.n_obj_done = 0, 0, 0
+
+    def seeds(self, k):
+        return [(k + 1) * 100003 + i for i in self.mine]  # new noise for every object of every step
+
+    def make_runner(self, k, engine, state=None):
+        from puzzlefusion_plusplus_b200.loop import BatchRunner, PerObjectNoise
+        w = self.w
+        return BatchRunner(engine, self.objects, max_iters=w["max_iters"], merge=w["merge"], verify_last=w["verify_last"],
+                           noise=PerObjectNoise(self.dev, self.seeds(k), w["ddpm_steps"]), trajectory=False, state=state,
+                           use_graph=not self.a.no_graph)
+
+    def make_state(self, slot=0):
+        from puzzlefusion_plusplus_b200.loop import BatchState
+        return BatchState(self.engines[slot], self.objects)
+
+    def run_steps(self, k0, n, states=None, count=False):
+        """n steps (batches k0 .. k0+n-1) through the slots; metric block of every batch, all-gathered per step."""
+        from puzzlefusion_plusplus_b200 import sharding
+        from puzzlefusion_plusplus_b200.loop import run_pipelined
+        from puzzlefusion_plusplus_b200.metrics import object_metrics
+        runners = {}
+
+        def mk(k, engine):
+            r = self.make_runner(k0 + k, engine, None if states is None else states[k])
+            runners[k] = r
+            return r
+        outs = run_pipelined(self.engines, self.streams, mk, n)
+        gathered = []
+        for k in range(n):
+            m = object_metrics(outs[k], self.objects, engine=self.engines[0]).to(self.dev)  # [B,4] per-object metrics
+            gathered.append(sharding.gather_metrics(m, self.mine, self.total))
+            if count:
+                self.obj_iters += sum(outs[k]["iters"])
+                self.frag_iters += runners[k].frag_iterations
+                self.n_obj_done += len(self.objects)
+        return gathered
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -272,125 +389,102 @@ def main():
         run_reference(a, rank)
         return
 
+    import gc
     import torch.distributed as dist
-    from puzzlefusion_plusplus_b200 import _lib, engine as engine_mod, loop as loop_mod, synthetic, weights as weights_mod
+    from puzzlefusion_plusplus_b200 import _lib, engine as engine_mod, loop as loop_mod, weights as weights_mod
     from puzzlefusion_plusplus_b200.engine import Engine
-    from puzzlefusion_plusplus_b200.loop import BatchRunner, BatchState, PerObjectNoise, run_interleaved
-    from puzzlefusion_plusplus_b200.metrics import object_metrics
+    from puzzlefusion_plusplus_b200.loop import BatchRunner, PerObjectNoise
 
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    P = max(20, a.frags)  # fragment slots per object (config 5: 64; PE tables extended accordingly)
-    ck = synthetic.make_checkpoints(0, max_parts=P)
-    n_str = max(1, min(a.streams, a.batch))
-    engines = [Engine(ck, num_inference_steps=a.ddpm_steps, precision=a.precision, device=dev, chunk_frags=a.chunk, max_parts=P)
-               for _ in range(n_str)]
-    eng = engines[0]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(n_str)]
-    # distinct objects per rank (weak scaling: per-GPU work fixed)
-    n_unique = min(a.batch, 8)
-    uniq = [synthetic.make_object(2000 + rank * 64 + i, num_parts=a.frags, n_points=a.points, max_parts=P)
-            for i in range(n_unique)]
-    objects = [uniq[i % n_unique] for i in range(a.batch)]
-    seeds = [rank * 10007 + i for i in range(a.batch)]
-    parts = [list(range(i, a.batch, n_str)) for i in range(n_str)]  # object indices per stream
     probe = KernelProbe(_lib)
     probe.install([engine_mod, loop_mod, weights_mod])
-
-    def make_states():
-        return [BatchState(engines[i], [objects[j] for j in parts[i]]) for i in range(n_str)]
-
-    def one_step(resident_states=None):
-        t_0 = time.perf_counter()
-        runners = [BatchRunner(engines[i], [objects[j] for j in parts[i]], max_iters=1,
-                               noise=PerObjectNoise(dev, [seeds[j] for j in parts[i]], a.ddpm_steps), trajectory=False,
-                               state=None if resident_states is None else resident_states[i], verify_last=True,
-                               use_graph=not a.no_graph)
-                   for i in range(n_str)]
-        t_a = time.perf_counter()
-        outs = run_interleaved(runners, streams)
-        t_b = time.perf_counter()
-        out = {k: torch.cat([outs[i][k] for i in range(n_str)]) for k in ("pred_trans", "pred_rots")}
-        order = [j for pl in parts for j in pl]
-        m = object_metrics(out, [objects[j] for j in order], engine=eng).to(dev)  # [B,4] per-object metric block
-        if os.environ.get("PFPP_BENCH_PHASES"):
-            torch.cuda.synchronize()
-            print(f"[phases] runners {1e3 * (t_a - t_0):.1f} ms, loop {1e3 * (t_b - t_a):.1f} ms, metrics "
-                  f"{1e3 * (time.perf_counter() - t_b):.1f} ms", file=sys.stderr)
-        if world > 1:
-            gathered = torch.empty(world * m.shape[0], m.shape[1], device=dev)
-            dist.all_gather_into_tensor(gathered, m)
-            m = gathered
-        return m
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing ----
-    # All one-time set-up (resident states, GC policy, NVML) comes BEFORE the warm-up steps, so that the W warm-up
-    # steps run in exactly the configuration of the timed steps and absorb every first-use cost.
-    one_step(make_states())  # sizes workspaces / captures the graph (not counted as warm-up)
-    states = [make_states() for _ in range(a.steps)]
-    # Host runtime policy for the timed regions (as a serving process would run): long-lived host objects
-    # (checkpoints, objects, pre-built states) are frozen out of the cyclic GC's working set and automatic
-    # collection is off while batches are in flight (re-enabled at the end).  With the collector on, random batch
-    # steps take 40-170 ms longer (measured, `ms_each_step`); PFPP_BENCH_GC=1 keeps it on.
-    import gc
-    gc.collect()
-    gc.freeze()
+    def measure(arm, steps, warmup, sampler=None):
+        """(device-timed objects/s with resident inputs, e2e objects/s from host tensors, elapsed ms, launches)"""
+        B = arm.w["batch"]
+        arm.run_steps(0, 1, [arm.make_state(0)])  # sizes workspaces / captures graphs (not counted as warm-up)
+        states = [arm.make_state(k % arm.n_slots) for k in range(steps)]
+        gc.collect()
+        gc.freeze()
+        for k in range(warmup):
+            arm.run_steps(1000 + k, 1, [arm.make_state(0)])
+        barrier()
+        launches0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx = sampler if sampler is not None else _Null()
+        with ctx:
+            e0.record()
+            arm.run_steps(0, steps, states, count=True)
+            e1.record()
+            barrier()
+        elapsed_ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count - launches0
+        t = torch.tensor([elapsed_ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        busy_ms, elapsed_ms = elapsed_ms, float(t.item())
+        value = B * world * steps / (elapsed_ms * 1e-3)
+        # ---- end-to-end: host tensors in, poses out ----
+        barrier()
+        w0 = time.perf_counter()
+        arm.run_steps(0, steps, None)
+        barrier()
+        t = torch.tensor([time.perf_counter() - w0], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = B * world * steps / float(t.item())
+        return value, e2e_value, elapsed_ms, launches, busy_ms
+
+    # Host runtime policy for the timed regions (as a serving process would run): long-lived host objects are frozen
+    # out of the cyclic GC's working set and automatic collection is off while batches are in flight (random batch
+    # steps take 40-170 ms longer with the collector on; PFPP_BENCH_GC=1 keeps it on).
     host_gc = "on" if os.environ.get("PFPP_BENCH_GC") else "frozen + disabled during the timed regions"
+    arm = Arm(a, a.w, rank, world, local, a.workload)
     if host_gc != "on":
         gc.disable()
     sampler = ClockSampler(None if a.no_clocks else local)
-    for _ in range(a.warmup):
-        one_step(make_states())
-    barrier()
-    launches0 = _lib.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with sampler as clk:
-        e0.record()
-        step_ev = []
-        for k in range(a.steps):
-            metrics = one_step(states[k])
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            step_ev.append(ev)
-        e1.record()
-        barrier()
-    per_step_ms = [a_.elapsed_time(b_) for a_, b_ in zip([e0] + step_ev[:-1], step_ev)]
-    elapsed_ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count - launches0
-    t = torch.tensor([elapsed_ms], device=dev)
+    value, e2e_value, elapsed_ms, launches, busy_ms = measure(arm, a.steps, a.warmup, sampler)
+    w, P, B = a.w, arm.P, a.w["batch"]
+    o = arm.objects[0]
+    h2d = sum(int(v.numel() * v.element_size()) for ob in arm.objects for k, v in ob.items()
+              if torch.is_tensor(v) and k in ("part_pcs", "part_scale", "part_trans", "part_rots", "part_pcs_by_area"))
+    iters_mean = arm.obj_iters / max(arm.n_obj_done, 1)
+    # per outer iteration: poses + one logit per fragment pair; final poses once
+    d2h = int(B * (iters_mean * (P * 7 * 4 + P * (P - 1) // 2 * 4) + P * 7 * 4))
+    stats = {"iterations_per_object": iters_mean,
+             "fragment_iterations_per_object": arm.frag_iters / max(arm.n_obj_done, 1),
+             "objects": arm.n_obj_done, "workload": workload_name(a)}
+    busy = torch.tensor([busy_ms], device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = a.batch * world * a.steps / (elapsed_ms * 1e-3)
+        allb = [torch.empty_like(busy) for _ in range(world)]
+        dist.all_gather(allb, busy)
+        busy_all = [float(b.item()) for b in allb]
+    else:
+        busy_all = [busy_ms]
 
-    # ---- end-to-end: host tensors in, poses out ----
-    barrier()
-    w0 = time.perf_counter()
-    for k in range(a.steps):
-        one_step(None)
-    barrier()
-    e2e_s = time.perf_counter() - w0
-    t = torch.tensor([e2e_s], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = a.batch * world * a.steps / float(t.item())
-    o = objects[0]
-    h2d = a.batch * sum(int(v.numel() * v.element_size()) for k, v in o.items() if torch.is_tensor(v) and k in (
-        "part_pcs", "part_scale", "part_trans", "part_rots", "part_pcs_by_area"))
-    d2h = a.batch * (P * 7 * 4 * 2 + P * (P - 1) // 2 * 4)  # poses (x, final) + one logit per fragment pair
+    secondary = None
+    if a.workload == "config3" and not a.no_secondary and world == 1:
+        a2 = argparse.Namespace(**vars(a))
+        a2.w = dict(WORKLOADS["config2"])
+        arm2 = Arm(a2, a2.w, rank, world, local, "config2")
+        v2, e2, ms2, _, _ = measure(arm2, max(2, a.steps // 2), 3)
+        secondary = {"config2": {"workload": workload_name(a2, a2.w, "config2"), "value": v2, "unit": UNIT,
+                                 "ms_per_step": ms2 / max(2, a.steps // 2), "e2e": e2}}
+        del arm2
 
     # ---- kernel probe: eager DDPM steps of the whole batch on one stream, events around every launch ----
     probe_steps = 3
-    eng_p = Engine(ck, num_inference_steps=a.ddpm_steps, precision=a.precision, device=dev, chunk_frags=a.chunk, max_parts=P)
-    runner = BatchRunner(eng_p, objects, max_iters=1, noise=PerObjectNoise(dev, seeds, a.ddpm_steps), trajectory=False,
-                         use_graph=False)
+    eng_p = Engine(arm.ck, num_inference_steps=w["ddpm_steps"], precision=a.precision, device=dev, chunk_frags=a.chunk, max_parts=P)
+    runner = BatchRunner(eng_p, arm.objects, max_iters=1, noise=PerObjectNoise(dev, arm.seeds(0), w["ddpm_steps"]),
+                         trajectory=False, use_graph=False)
     runner.begin_iteration()
     runner._launch_step()  # sizes the workspaces
     torch.cuda.synchronize()
@@ -409,28 +503,12 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    if a.precision == "bf16":
+    if a.precision != "fp32":
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "measured (sustained bf16, MEASURED_PEAKS.json)" if peaks else "fallback"
     else:
         peak = 72.0  # fp32 FFMA nominal: 148 SM x 128 lanes x 2 x 1.9 GHz (no measured fp32 peak is provided)
         peak_src = "nominal fp32 FFMA"
-    def ncu_traffic(entry):
-        """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-        `ncu --set full` capture of this command (profiles/r1e_sa / r1d_gemm / r1e_attention _full_summary.txt); None if there is no capture."""
-        fname = {"pfpp_sa_fused": "r1e_sa_full_summary.txt", "pfpp_gemm_bf16": "r1d_gemm_full_summary.txt",
-                 "pfpp_attention_tc": "r1e_attention_full_summary.txt"}.get(entry)
-        try:
-            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            tot, n = 0.0, 0
-            for ln in open(os.path.join(ROOT, "profiles", fname)):
-                f = ln.split()
-                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    tot += float(f[1]) * unit[f[2].strip("[]")]
-                    n += f[0] == "dram__bytes_read.sum"
-            return tot / n if n else None
-        except Exception:
-            return None
 
     tensor_kernels = {k: v for k, v in kernels.items() if v["tflops"]}
     dom = max(tensor_kernels, key=lambda k: tensor_kernels[k]["ms_per_ddpm_step"])
@@ -438,40 +516,73 @@ def main():
         v["share_of_ddpm_step"] = v["ms_per_ddpm_step"] / probe_step_ms
         v["frac_of_peak"] = (v["tflops"] / peak) if v["tflops"] else None
     step_flops = sum(v["tflops"] * 1e12 * v["ms_per_ddpm_step"] * 1e-3 for v in tensor_kernels.values())
-    ddpm_ms_timed = elapsed_ms / a.steps / a.ddpm_steps
+    dtype = {"bf16": "bf16", "fp32": "f32", "tc32": "bf16x3 (hi/lo split operands, fp32 accumulate)"}[a.precision]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": elapsed_ms / a.steps, "ms_each_step": [round(v, 1) for v in per_step_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if a.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "precision_mode": a.precision, "streams": n_str, "host_gc": host_gc,
-                   "l2": "per-step working set (activations of one fragment chunk) exceeds L2; inputs differ per step"},
+        "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic",
+        "config": {"workload": workload_name(a), "precision_mode": a.precision, "slots": arm.n_slots, "host_gc": host_gc,
+                   "outer_iterations_per_object": round(iters_mean, 3),
+                   "fragment_iterations_per_object": round(stats["fragment_iterations_per_object"], 2),
+                   "sharding": "puzzlefusion_plusplus_b200.sharding.shard_objects / gather_metrics",
+                   "rank_busy_ms": [round(b, 1) for b in busy_all],
+                   "l2": "per-step working set (activations of one batch) exceeds L2; new noise seeds every step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
-        "clocks": clk.summary(),
+        "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
                      "frac": kernels[dom]["tflops"] / peak if peak else None, "traffic": ncu_traffic(dom),
                      "traffic_note": "DRAM bytes per launch (read + write), mean over the launches captured in profiles/*_full_summary.txt",
                      "peak_source": peak_src,
                      "avg_launch_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["share_of_ddpm_step"],
                      "whole_step": {"algorithmic_tflop_per_ddpm_step": step_flops / 1e12,
-                                    "achieved_tflops_timed_region": step_flops / (ddpm_ms_timed * 1e-3) / 1e12,
-                                    "frac_of_peak": step_flops / (ddpm_ms_timed * 1e-3) / 1e12 / peak},
-                     "note": "dominant kernel = largest share of the DDPM step; per-launch CUDA events in an eager "
-                             "single-stream probe pass inside bench.py right after the timed region (the timed region "
-                             "replays CUDA graphs); FLOPs are algorithmic (masked work not counted)"},
+                                    "probe_ms_per_ddpm_step": probe_step_ms,
+                                    "achieved_tflops_probe": step_flops / (probe_step_ms * 1e-3) / 1e12,
+                                    "frac_of_peak": step_flops / (probe_step_ms * 1e-3) / 1e12 / peak},
+                     "note": "dominant kernel = largest share of the DDPM step of the first outer iteration (all "
+                             "objects active); per-launch CUDA events in an eager single-stream probe pass inside "
+                             "bench.py right after the timed region (the timed region replays CUDA graphs); FLOPs are "
+                             "algorithmic (masked work not counted); set-abstraction levels are listed separately"},
         "kernels": kernels,
     }
+    if secondary:
+        line["secondary"] = secondary
     gc.enable()
     if rank == 0:
+        if a.workload == "config3" and world == 1 and os.environ.get("PFPP_WRITE_STATS"):
+            json.dump(stats, open(STATS_FILE, "w"), indent=1)
         if not a.no_cpu_baseline and world == 1:
-            v, t_step, t_verify = cpu_objects_per_sec(a, a.cpu_sample_steps)
-            line["cpu_baseline"] = {
-                "value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                "sample": f"{a.cpu_sample_steps} of {a.ddpm_steps} DDPM steps + 1 verifier pass of one object, "
-                          f"extrapolated; {t_step * 1e3:.0f} ms/DDPM step"}
+            v, sample = cpu_objects_per_sec(a, a.cpu_sample_steps, stats if w["merge"] else None)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def ncu_traffic(entry):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/*_full_summary.txt); None if there is no capture."""
+    fname = {"pfpp_sa_fused": "r1e_sa_full_summary.txt", "pfpp_gemm_bf16": "r1d_gemm_full_summary.txt",
+             "pfpp_attention_tc": "r1e_attention_full_summary.txt"}.get(entry.split("[")[0])
+    try:
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot, n = 0.0, 0
+        for ln in open(os.path.join(ROOT, "profiles", fname)):
+            f = ln.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * unit[f[2].strip("[]")]
+                n += f[0] == "dram__bytes_read.sum"
+        return tot / n if n else None
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":

@@ -206,6 +206,25 @@ int pfpp_verifier_head(const float* h, const int* tok_row, int n_tokens, const f
 int pfpp_merge_filter(const float* pcs, int n_clouds, int n_points, int knn, float threshold, unsigned char* keep,
                       float* normals, cudaStream_t stream);
 
+/* The whole merge stage of one outer iteration (auto_aggl.py:234-286: merge_node, by-area shift,
+ * remove_intersect_points_and_fps_ds, renormalisation; utils/node_merge_utils.py:125-135,159-222) for ALL
+ * connected components of ALL objects of a batch, asynchronously on `stream`, no host round trip.
+ *   posed [slots,N,3]: fragment clouds posed by pfpp_pose_apply(normalise=1, seg_scale);
+ *   comp_start [n_comp+1] -> member_slot [n_clouds] (valid members of component c, concatenation order),
+ *   member_comp [n_clouds], comp_pivot_slot [n_comp]; pair_i/pair_j [n_pairs]: ordered pairs (i != j) of member-list
+ *   indices inside one component; uniform [n_comp]: the torch.rand(1) draws of the random-start FPS (nmu:219);
+ *   area segments: by_area[seg] = by_area_posed[seg] - centroid[area_seg_comp] (auto_aggl.py:259-262).
+ * Writes part_pcs[pivot slot] = ds / max|ds|, scale[pivot slot] = max|ds| and result [n_comp,8] =
+ * {centroid xyz, max|ds|, kept points M, n_out = ceil(M * float32(N/M)), fps start, 0} (floats).
+ * workspace >= pfpp_merge_workspace_bytes(n_clouds, n_comp, n_points). */
+size_t pfpp_merge_workspace_bytes(int n_clouds, int n_comp, int n_points);
+int pfpp_merge(const float* posed, int n_points, int n_comp, int n_clouds, const int* comp_start,
+               const int* member_slot, const int* member_comp, const int* comp_pivot_slot, int n_pairs,
+               const int* pair_i, const int* pair_j, const float* uniform, float threshold, int knn,
+               int n_area_segs, const int* area_seg_start, const int* area_seg_len, const int* area_seg_comp,
+               const float* by_area_posed, float* by_area, float* part_pcs, float* scale, float* result,
+               void* workspace, size_t ws_bytes, cudaStream_t stream);
+
 /* chamferdist / pytorch3d knn_points(K=1) squared distances for the evaluation metrics
  * (denoiser/evaluation/evaluator.py:108,137): out[b,i] = min_j |a[b,i] - b[b,j]|^2. */
 int pfpp_nn_sqdist(const float* a, const float* b, int batches, int N, int M, float* out, cudaStream_t stream);

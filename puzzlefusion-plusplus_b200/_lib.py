@@ -50,7 +50,11 @@ SIGNATURES = {
     "pfpp_verifier_head": [_P, _P, _I, _P, _P, _I, _P, _P],
     "pfpp_merge_filter": [_P, _I, _I, _I, _F, _P, _P, _P],
     "pfpp_nn_sqdist": [_P, _P, _I, _I, _I, _P, _P],
+    "pfpp_merge": [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                   ctypes.c_size_t, _P],
 }
+# entry points that return a size instead of a status (no stream argument)
+SIZE_FUNCS = {"pfpp_merge_workspace_bytes": [_I, _I, _I]}
 
 _lib = None
 
@@ -73,6 +77,10 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
+    for name, argtypes in SIZE_FUNCS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_size_t
     _lib = lib
     return lib
 

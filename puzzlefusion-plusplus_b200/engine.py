@@ -38,7 +38,8 @@ class Engine:
     _FUSED_LEVELS = {(32, 0, 64, 64, 128): 1, (64, 128, 128, 128, 256): 2, (64, 256, 256, 256, 512): 3}
 
     def __init__(self, ckpt, num_inference_steps=20, precision="bf16", device="cuda:0", num_layers=6, heads=8,
-                 max_parts=20, latent_points=25, latent_dim=64, verifier_layers=6, sa_cfg=SA_CFG, chunk_frags=32):
+                 max_parts=20, latent_points=25, latent_dim=64, verifier_layers=6, sa_cfg=SA_CFG, chunk_frags=32,
+                 freeze_gc=False):
         if not torch.cuda.is_available():
             raise _lib.PfppError("pfpp-b200 needs a CUDA device (sm_100a); there is no CPU path")
         if precision not in ("bf16", "fp32"):
@@ -67,12 +68,12 @@ class Engine:
         self._ws = {}
         self._ws_version = 0
         self._step_ctx = {}  # loop.StepContext cache: persistent step buffers + captured graph per batch geometry
-        # The checkpoints, packed weights and synthetic/real objects are long-lived: move everything allocated so
-        # far into the permanent generation so that the cyclic GC's full collections (triggered by the small host
-        # objects of the agglomeration loop) do not re-traverse them -- measured: ~100 ms pauses per batch of 32
-        # objects (20 % of a batch step) without this.
-        gc.collect()
-        gc.freeze()
+        if freeze_gc:
+            # Opt-in, process-wide: move everything allocated so far (checkpoints, packed weights, objects) into the
+            # permanent generation so that the cyclic GC's full collections, triggered by the small host objects of
+            # the agglomeration loop, do not re-traverse them -- measured ~100 ms pauses per batch of 32 objects.
+            gc.collect()
+            gc.freeze()
 
     # ------------------------------------------------------------------ helpers
     def buf(self, name, shape, dtype):
@@ -108,6 +109,44 @@ class Engine:
         ev.record()
         self._ws[("pin_ev", name)] = ev
         return dev_t
+
+    def upload_array(self, name, arr):
+        """Small host table (numpy) -> fresh device tensor of the same shape / dtype, through a persistent pinned
+        staging buffer, asynchronously on the current stream."""
+        src = torch.from_numpy(np.ascontiguousarray(arr))
+        n = src.numel()
+        key = ("pin", name)
+        st = self._ws.get(key)
+        if st is None or st.numel() < n or st.dtype != src.dtype:
+            st = torch.empty(max(n, 64), dtype=src.dtype).pin_memory()
+            self._ws[key] = st
+        ev = self._ws.get(("pin_ev", name))
+        if ev is not None:
+            ev.synchronize()
+        view = st[:n].view(src.shape)
+        view.copy_(src)
+        dev_t = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+        dev_t.copy_(view, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._ws[("pin_ev", name)] = ev
+        return dev_t
+
+    def download(self, tensors):
+        """ONE device->host read: every tensor of the dict is copied asynchronously into a persistent pinned buffer,
+        then the current stream is synchronised once.  Returns host copies."""
+        views = {}
+        for name, t in tensors.items():
+            n = t.numel()
+            key = ("pin_d", name)
+            st = self._ws.get(key)
+            if st is None or st.numel() < n or st.dtype != t.dtype:
+                st = torch.empty(max(n, 64), dtype=t.dtype).pin_memory()
+                self._ws[key] = st
+            views[name] = st[:n].view(t.shape)
+            views[name].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return {k: v.clone() for k, v in views.items()}
 
     def gemm(self, a, lda, lin, out, ldc, M, epi=EPI_NONE, residual=None, ldr=0, out_bf16=None, force_f32=False):
         """out[M, N'] = epi(a[M,K] @ W^T + b) (+ residual) on the engine selected by the precision mode."""

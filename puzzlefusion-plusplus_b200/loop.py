@@ -14,6 +14,7 @@ C.10) and are left untouched here.
 """
 import gc
 import itertools
+import time
 
 import networkx as nx
 import numpy as np
@@ -36,13 +37,14 @@ class GlobalTorchNoise:
     def initial(self, B, P):
         return torch.randn((B, P, 7), device=self.device)
 
-    def iteration_noise(self, B, P, timesteps):
+    def iteration_noise(self, B, P, timesteps, active=None):
         rows = [torch.randn((B, P, 7), device=self.device) if t > 0 else torch.zeros((B, P, 7), device=self.device)
                 for t in timesteps]
         return torch.stack(rows).reshape(len(timesteps), B * P, 7).contiguous()
 
-    def fps_start(self, b, M):
-        return int((torch.rand(1, device=self.device) * float(M)).to(torch.int64))
+    def fps_uniform(self, b):
+        """the torch.rand(1) of node_merge_utils.py:219 as a DEVICE scalar (start = int(u * M) is taken on the device)"""
+        return torch.rand(1, device=self.device)
 
 
 class ReplayNoise:
@@ -56,14 +58,13 @@ class ReplayNoise:
     def initial(self, B, P):
         return self.normals.pop(0).reshape(B, P, 7).clone()
 
-    def iteration_noise(self, B, P, timesteps):
+    def iteration_noise(self, B, P, timesteps, active=None):
         rows = [self.normals.pop(0).reshape(B, P, 7) if t > 0 else torch.zeros((B, P, 7), device=self.device)
                 for t in timesteps]
         return torch.stack(rows).reshape(len(timesteps), B * P, 7).contiguous()
 
-    def fps_start(self, b, M):
-        u = self.uniforms.pop(0)
-        return int((u.to(torch.float32) * float(M)).to(torch.int64))
+    def fps_uniform(self, b):
+        return self.uniforms.pop(0).to(torch.float32).reshape(1).to(self.device)
 
 
 class PerObjectNoise:
@@ -77,13 +78,13 @@ class PerObjectNoise:
     def initial(self, B, P):
         return torch.cat([torch.randn((1, P, 7), device=self.device, generator=g) for g in self.gens], 0)
 
-    def iteration_noise(self, B, P, timesteps):
+    def iteration_noise(self, B, P, timesteps, active=None):
         T = len(timesteps)
         cur = torch.stack([torch.randn((T, P, 7), device=self.device, generator=g) for g in self.gens], 1)
         return cur.reshape(T, B * P, 7).contiguous()
 
-    def fps_start(self, b, M):
-        return int((torch.rand(1, device=self.device, generator=self.gens[b]) * float(M)).to(torch.int64))
+    def fps_uniform(self, b):
+        return torch.rand(1, device=self.device, generator=self.gens[b])
 
 
 def _triu_index(P):
@@ -122,6 +123,8 @@ class BatchState:
             self.graph.append(g)
         self.classified = np.zeros((B, P), dtype=bool)
         self.done = [False] * B
+        self.pending = []          # merges whose centroid / scale have not been read back yet (see _resolve_pending)
+        self.pending_result = None
         self.has_matching = all("part_pcs_by_area" in o for o in objects)
         if self.has_matching:
             self._build_matching(objects, dev)
@@ -136,9 +139,11 @@ class BatchState:
         for b, o in enumerate(objects):
             pts.append(o["part_pcs_by_area"].float())
             m = o.get("_pfpp_matching")
-            if m is None:
+            key = (id(o["edges"]), id(o["correspondences"]), id(o["critical_pcs_idx"]), P)
+            if m is None or m[0] != key:
                 # object-local tables (offsets relative to the object's by-area cloud / edge-row block); they depend
-                # only on the object, so they are built once and kept on the object dict
+                # only on the object, so they are built once and kept with the object dict (re-built when the edge /
+                # correspondence containers or the slot count they were built from are replaced)
                 n_pcs = np.asarray(o["n_pcs"]).astype(np.int64)
                 cs = np.concatenate([[0], np.cumsum(n_pcs)])
                 crit = np.asarray(o["critical_pcs_idx"]).astype(np.int64)
@@ -146,16 +151,19 @@ class BatchState:
                 src_l, tgt_l, len_l, row_l = [], [], [], []
                 for e in range(edges.shape[0]):
                     idx2, idx1 = int(edges[e, 0]), int(edges[e, 1])
+                    if idx1 >= idx2:
+                        # the reference writes edge_features[0, idx1, idx2] and then keeps the strict upper triangle
+                        # only (auto_aggl.py:193-196): such an entry never reaches the verifier
+                        continue
                     corr = np.asarray(o["correspondences"][e]).reshape(-1, 2)
                     src_l.append(cs[idx1] + crit[cs[idx1] + corr[:, 0]])
                     tgt_l.append(cs[idx2] + crit[cs[idx2] + corr[:, 1]])
                     len_l.append(corr.shape[0])
                     row_l.append(tri[(idx1, idx2)])
                 cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, dtype=np.int64)  # noqa: E731
-                m = (cs, cat(src_l), cat(tgt_l), np.asarray(len_l, dtype=np.int64), np.asarray(row_l, dtype=np.int64), P)
+                m = (key, cs, cat(src_l), cat(tgt_l), np.asarray(len_l, dtype=np.int64), np.asarray(row_l, dtype=np.int64))
                 o["_pfpp_matching"] = m
-            cs, src, tgt, lens, rows, p_built = m
-            assert p_built == P, "object tables were built for another slot count"
+            _, cs, src, tgt, lens, rows = m
             self.area_base.append(base)
             self.area_cs.append(cs)
             pair_src.append(base + src)
@@ -177,6 +185,7 @@ class BatchState:
         self.n_edges = int(len(e_start))
         self.max_pairs = int(e_len.max()) if len(e_len) else 0
         self.tri_list = list(itertools.combinations(range(P), 2))
+        self.tri_np = np.asarray(self.tri_list, dtype=np.int64)  # [E_full, 2]
 
 
 class StepContext:
@@ -189,7 +198,7 @@ class StepContext:
     and engine and replayed for every later batch of that geometry from step 0 on -- no eager step, no capture, no
     graph construction / destruction per batch (those cost ~3 ms per batch and leave the GPU idle whenever the host
     stalls during them)."""
-    MAX_CACHED = 6
+    MAX_CACHED = 48  # ~12 MB each at 32 objects x 20 slots x 1000 points, T = 100
 
     def __init__(self, e, slots, N, F, n_obj):
         dev, T = e.device, e.T
@@ -208,6 +217,7 @@ class StepContext:
         self.scale = torch.empty(slots, **f32)
         self.graph = None
         self.ws_version = -1
+        self.owner = None  # the live BatchRunner whose poses / noise / clouds these buffers currently hold
 
     @staticmethod
     def get(e, slots, N, F, n_obj, max_global):
@@ -267,22 +277,23 @@ class BatchRunner:
         self.x_hist = None if self.use_graph else torch.empty(max_iters * engine.T, B * P, 7, device=dev)
         self.traj = [[] for _ in range(B)]
         self.iters = [0] * B
+        self.frag_iterations = 0
         self.timesteps = [int(t) for t in engine.sched.timesteps]
         self.step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
         self.it = 0
         self.graph = None
+        self.ctx = None
         self._cap_stream = None
         self.finished = False
 
     # -- phase 1 ---------------------------------------------------------------------------------
     def begin_iteration(self):
         st, e = self.st, self.e
-        if self.finished or self.it >= self.max_iters:
-            self.finished = True
+        if self.finished:
             return False
         self.active = [b for b in range(st.B) if not st.done[b]]
-        if not self.active:
-            self.finished = True
+        if self.it >= self.max_iters or not self.active:
+            self._finish()
             return False
         P = e.P
         slots, counts = [], []
@@ -291,12 +302,17 @@ class BatchRunner:
             slots += s
             counts.append(len(s))
         self.F = len(slots)
+        self.frag_iterations += self.F  # workload statistic: valid fragments x outer iterations they take part in
         frag_slot = torch.as_tensor(np.asarray(slots, dtype=np.int32))
-        noise_all = self.noise.iteration_noise(st.B, P, self.timesteps)
+        noise_all = self.noise.iteration_noise(st.B, P, self.timesteps, self.active)
         if self.use_graph:
             # persistent buffers + cached graph of this batch geometry: copy this iteration's inputs in
             max_global = int(max(counts)) * e.L
             ctx = self.ctx = StepContext.get(e, st.B * P, st.N, self.F, len(counts), max_global)
+            if ctx.owner is not None and ctx.owner is not self and not ctx.owner.finished:
+                raise _lib.PfppError("two live BatchRunners of the same batch geometry share one Engine: its step "
+                                     "buffers and CUDA graph cannot serve both (one Engine per concurrent batch)")
+            ctx.owner = self
             ctx.frag_slot.copy_(frag_slot)
             starts = np.concatenate([[0], np.cumsum(counts)[:-1]]) * e.L
             ctx.loc[0].copy_(torch.arange(self.F, dtype=torch.int32) * e.L)
@@ -379,53 +395,100 @@ class BatchRunner:
         self.si += 1
 
     # -- phase 3 ---------------------------------------------------------------------------------
+    def enqueue_verify(self):
+        """Device half of phase 3 (no host synchronisation): the verify stage of this outer iteration, enqueued right
+        behind its last DDPM step.  end_iteration() calls it when the caller has not."""
+        st, e = self.st, self.e
+        last = self.it + 1 == self.max_iters
+        # verify_last: BASELINE config 2 = one denoise pass + one verifier pass (no merge, no second pass)
+        self._verify = (not last) or self.verify_last
+        if self._verify and not st.has_matching:
+            raise _lib.PfppError("the verify stage needs the matching data of every object (part_pcs_by_area, n_pcs, "
+                                 "critical_pcs_idx, edges, correspondences); run with max_iters=1 for the denoiser only")
+        self._verify_out = _verify_enqueue(e, st, self.active, self.x) if self._verify else None
+        self._verify_it = self.it
+
     def end_iteration(self):
+        """Verify stage on the device, ONE device->host read (poses, verifier logits, DDPM-step history, the
+        centroids / scales of the previous iteration's merges), host decisions on the <= 20-node graphs, then the
+        batched merge stage enqueued asynchronously (its results are read back with the next iteration's poses)."""
         st, e = self.st, self.e
         B, P, T = st.B, e.P, e.T
         for b in self.active:
             self.iters[b] += 1
-        x_host = self.x.cpu().reshape(B, P, 7)  # the one D2H read of this outer iteration
+        last = self.it + 1 == self.max_iters
+        if getattr(self, "_verify_it", -1) != self.it:
+            self.enqueue_verify()
+        verify = self._verify
+        want = {"x": self.x}
+        if verify:
+            want["logits"], feat = self._verify_out
         if self.trajectory:
-            xh = self.hist[:T].cpu().reshape(T, B, P, 7)
+            want["hist"] = self.hist[:T]
+        if st.pending:
+            want["merge"] = st.pending_result
+        host = e.download(want)
+        x_host = host["x"].reshape(B, P, 7)
+        _resolve_pending(st, host.get("merge"))
+        if self.trajectory:
+            xh = host["hist"].reshape(T, B, P, 7)
             for b in self.active:
                 self.traj[b].append(compose_params_steps(xh[:, b], st.pivot[b], st.init_pose[b]))
-        last = self.it + 1 == self.max_iters
-        if last and not self.verify_last:
-            self.finished = True
-            return
-        # verify_last: BASELINE config 2 = one denoise pass + one verifier pass (no merge, no second pass)
-        _verify_and_merge(e, st, self.active, self.x, x_host, self.ref_dev, self.ref_pose, self.threshold, self.noise,
-                          self.merge and not last, self.record)
+        if verify:
+            logits_h = host["logits"].reshape(B, st.E_full)
+            if self.record is not None:
+                self.record.append({"verify": True, "edge_features": feat.clone().reshape(B, st.E_full, 7),
+                                    "logits": logits_h.clone()})
+            _decide_and_merge(e, st, self.active, self.x, x_host, logits_h, self.ref_dev, self.ref_pose, self.threshold,
+                              self.noise, self.merge and not last, self.record)
         self.it += 1
-        if last:
-            self.finished = True
+        if last or all(st.done):
+            self._finish()
+
+    def _finish(self):
+        self.finished = True
+        if self.ctx is not None:
+            # the StepContext's buffers belong to the next batch of this geometry from now on
+            self.x = self.x.clone()
+            if self.ctx.owner is self:
+                self.ctx.owner = None
 
     def result(self):
         st, e = self.st, self.e
         B, P = st.B, e.P
-        x_host = self.x.cpu().reshape(B, P, 7)
+        want = {"x": self.x}
+        if st.pending:
+            want["merge"] = st.pending_result
+        host = e.download(want)
+        _resolve_pending(st, host.get("merge"))
+        x_host = host["x"].reshape(B, P, 7)
         pred_t, pred_r = compose_params_batch(x_host, st.pivot, st.init_pose, st.num_parts)
         return {"x": x_host, "pred_trans": pred_t, "pred_rots": pred_r,
                 "trajectory": [torch.cat(t) if t else torch.zeros(0) for t in self.traj], "iters": self.iters,
                 "pivots": st.pivot, "ref_part": torch.as_tensor(st.ref), "part_valids": torch.as_tensor(st.valid)}
 
 
-def run_interleaved(runners, streams=None):
+def run_interleaved(runners, streams=None, pause_gc=False):
     """Advance several BatchRunners in lock-step from one host thread, runner i on streams[i]: the
-    latency-bound geometry kernels of one batch overlap the tensor-core kernels of another."""
+    latency-bound geometry kernels of one batch overlap the tensor-core kernels of another.  Every runner needs
+    its OWN Engine (workspaces, step buffers and captured graphs are per engine).
+
+    pause_gc: switch Python's cyclic collector off while batches are in flight (a full collection costs tens of ms
+    and stalls the launch queue); opt-in because it is a process-wide setting."""
+    if len({id(r.e) for r in runners}) != len(runners):
+        raise _lib.PfppError("run_interleaved: every BatchRunner needs its own Engine (one Engine per concurrent batch)")
     cur = torch.cuda.current_stream()
     streams = streams or [cur] * len(runners)
     for s_ in streams:
         if s_ is not cur:
             s_.wait_stream(cur)
-    # no cyclic-GC pauses while kernels are being enqueued (a full collection costs tens of ms and stalls the GPU
-    # queue); the small host objects of this loop are reclaimed after the run
     gc_was_enabled = gc.isenabled()
-    gc.disable()
+    if pause_gc:
+        gc.disable()
     try:
         _advance(runners, streams)
     finally:
-        if gc_was_enabled:
+        if pause_gc and gc_was_enabled:
             gc.enable()
     for s_ in streams:
         if s_ is not cur:
@@ -451,6 +514,65 @@ def _advance(runners, streams):
                 r.end_iteration()
 
 
+def run_pipelined(engines, streams, make_runner, n_batches, poll_s=2e-4):
+    """Feed `n_batches` batches through len(engines) SLOTS (one Engine + one CUDA stream each) from one host thread.
+
+    make_runner(k, engine) -> BatchRunner of batch k.  Every slot always has one whole outer iteration (T graph
+    replays + the verify stage) enqueued; the host services whichever slot's iteration finishes first (CUDA event
+    poll): its single device->host read, the graph decisions, the batched merge, then the next iteration -- or the
+    next batch when this one is finished.  Objects leave the loop after different numbers of outer iterations
+    (auto_aggl.py:224-232,287-289), so the late iterations of a batch hold few fragments and cannot fill the GPU;
+    here they run under the early, full iterations of the next batch on the other slot.  Returns results in batch order."""
+    n = len(engines)
+    if len({id(e) for e in engines}) != n:
+        raise _lib.PfppError("run_pipelined: one Engine per slot")
+    cur = torch.cuda.current_stream()
+    for s_ in streams:
+        s_.wait_stream(cur)
+    slots, events = [None] * n, [None] * n
+    results = [None] * n_batches
+    next_batch = 0
+
+    def advance(i):
+        """slot i: start the next outer iteration (fetching the next batch when needed) and enqueue all of it"""
+        nonlocal next_batch
+        with torch.cuda.stream(streams[i]):
+            while True:
+                r = slots[i]
+                if r is None:
+                    if next_batch >= n_batches:
+                        events[i] = None
+                        return
+                    r = slots[i] = make_runner(next_batch, engines[i])
+                    r.batch_index = next_batch
+                    next_batch += 1
+                if r.begin_iteration():
+                    break
+                results[r.batch_index] = r.result()
+                slots[i] = None
+            for _ in range(r.e.T):
+                r.step()
+            r.enqueue_verify()
+            ev = torch.cuda.Event()
+            ev.record()
+            events[i] = ev
+
+    for i in range(n):
+        advance(i)
+    while any(ev is not None for ev in events):
+        ready = [i for i, ev in enumerate(events) if ev is not None and ev.query()]
+        if not ready:
+            time.sleep(poll_s)
+            continue
+        i = ready[0]
+        with torch.cuda.stream(streams[i]):
+            slots[i].end_iteration()
+        advance(i)
+    for s_ in streams:
+        cur.wait_stream(s_)
+    return results
+
+
 def run_batch(engine, objects, max_iters, threshold=0.9, noise=None, merge=True, record=None, trajectory=True,
               state=None, verify_last=False, use_graph=True):
     """Run the full loop on a list of per-object dicts (no batch dim).
@@ -463,31 +585,36 @@ def run_batch(engine, objects, max_iters, threshold=0.9, noise=None, merge=True,
     return run_interleaved([r])[0]
 
 
-def _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshold, noise, merge, record):
-    """auto_aggl.py:156-289 for all active objects."""
-    dev, P, B, N = engine.device, st.P, st.B, st.N
-    i32 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int32).reshape(-1)).to(dev)  # noqa: E731
-    # ---- pose the by-area cloud with the (un-normalised) pivot poses: node_merge_utils.py:16-41
-    seg_s, seg_l, seg_p = [], [], []
-    for b in active:
-        cs, base = st.area_cs[b], st.area_base[b]
-        for i in range(st.num_parts[b]):
-            seg_s.append(base + cs[i])
-            seg_l.append(cs[i + 1] - cs[i])
-            seg_p.append(b * P + st.pivot[b][i])
-    seg_s, seg_l, seg_p = i32(seg_s), i32(seg_l), i32(seg_p)
-    call("pfpp_pose_apply", st.by_area.data_ptr(), seg_s.data_ptr(), seg_l.data_ptr(), seg_p.data_ptr(), x.data_ptr(),
-         None, 0, seg_s.numel(), st.by_area_T.data_ptr())
-    # ---- edge histograms + verifier
+def _verify_enqueue(engine, st, active, x):
+    """auto_aggl.py:156-206 for all active objects, device work only: pose the by-area clouds with the
+    (un-normalised) pivot poses, per-edge Chamfer histograms, verifier transformer.  Returns (logits [B*E_full]
+    device, edge features [B*E_full, 7] device)."""
+    dev, P, B = engine.device, st.P, st.B
+    # packed tables of the active objects: depend only on (active set, pivots) -> cached on the state
+    key = (tuple(active), tuple(tuple(st.pivot[b]) for b in active))
+    if getattr(st, "_seg_key", None) != key:
+        seg_s, seg_l, seg_p = [], [], []
+        for b in active:
+            cs, base, n = st.area_cs[b], st.area_base[b], st.num_parts[b]
+            seg_s.append(base + cs[:n])
+            seg_l.append(cs[1:n + 1] - cs[:n])
+            seg_p.append(b * P + np.asarray(st.pivot[b][:n], dtype=np.int64))
+        tab = np.stack([np.concatenate(seg_s), np.concatenate(seg_l), np.concatenate(seg_p)]).astype(np.int32)
+        st._seg = engine.upload_array("verify_segs", tab)
+        st._seg_key = key
+    seg = st._seg
+    n_seg = seg.shape[1]
+    call("pfpp_pose_apply", st.by_area.data_ptr(), seg[0].data_ptr(), seg[1].data_ptr(), seg[2].data_ptr(), x.data_ptr(),
+         None, 0, n_seg, st.by_area_T.data_ptr())
     n_rows = B * st.E_full
     feat = engine.buf("edge_feat", (n_rows, 7), torch.float32)
     call("pfpp_edge_features", st.by_area_T.data_ptr(), st.pair_src.data_ptr(), st.pair_tgt.data_ptr(),
          st.e_start.data_ptr(), st.e_len.data_ptr(), st.e_row.data_ptr(), st.n_edges, max(st.max_pairs, 1), n_rows,
          feat.data_ptr())
-    # packed valid-edge tokens of the active objects: depends only on (active, num_parts) -> cached on the state
-    key = tuple(active)
-    if getattr(st, "_tok_key", None) != key:
-        tri = np.asarray(st.tri_list, dtype=np.int64)  # [E_full, 2]
+    # packed valid-edge tokens of the active objects: depends only on (active, num_parts)
+    tkey = tuple(active)
+    if getattr(st, "_tok_key", None) != tkey:
+        tri = st.tri_np
         rows, ii, jj, seg_start, seg_len = [], [], [], [], []
         pos = 0
         for b in active:
@@ -499,124 +626,135 @@ def _verify_and_merge(engine, st, active, x, x_host, ref_dev, ref_pose, threshol
             seg_start.append(pos)
             seg_len.append(len(e))
             pos += len(e)
-        st._tok = (i32(np.concatenate(rows)), i32(np.concatenate(ii)), i32(np.concatenate(jj)), i32(seg_start), i32(seg_len),
-                   max(seg_len))
-        st._tok_key = key
+        tok = engine.upload_array("verify_tok", np.stack([np.concatenate(rows), np.concatenate(ii),
+                                                           np.concatenate(jj)]).astype(np.int32))
+        sg = engine.upload_array("verify_tok_seg", np.asarray([seg_start, seg_len], dtype=np.int32))
+        st._tok = (tok[0], tok[1], tok[2], sg[0], sg[1], max(seg_len))
+        st._tok_key = tkey
     tok_row, tok_i, tok_j, seg_start_d, seg_len_d, max_seg = st._tok
     logits = engine.verifier_logits(feat, tok_row, tok_i, tok_j, seg_start_d, seg_len_d, max_seg, n_rows)
-    logits_h = logits.cpu().reshape(B, st.E_full)  # D2H (syncs)
-    if record is not None:
-        record.append({"verify": True, "edge_features": feat.clone().reshape(B, st.E_full, 7), "logits": logits_h.clone()})
-    pred = torch.sigmoid(logits_h) > threshold  # auto_aggl.py:204-205 (edge validity applied below)
-    pred_np = pred.numpy()
-    tri_np = np.asarray(st.tri_list, dtype=np.int64)
+    return logits, feat
+
+
+def _decide_and_merge(engine, st, active, x, x_host, logits_h, ref_dev, ref_pose, threshold, noise, merge, record):
+    """auto_aggl.py:204-289 for all active objects: accept edges, promote reference parts, gate merges (host, on the
+    <= 20-node graphs), then ONE batched device merge for every component of every object."""
+    dev, P, B = engine.device, st.P, st.B
+    pred_np = (torch.sigmoid(logits_h) > threshold).numpy()  # auto_aggl.py:204-205 (edge validity applied below)
+    tri_np = st.tri_np
     # reference_gt_and_rots = x.clone() (auto_aggl.py:222) for active objects
     ref_pose.copy_(x)
-
-    # ---- posed fragment clouds for merging: node_merge_utils.py:43-53 (normalised quaternion)
-    posed = None
+    comps = []  # (object, nodes of the component, valid members in concatenation order, pivot)
     for b in active:
         n = st.num_parts[b]
-        ref_idx = [p for p in range(P) if st.ref[b, p]]
+        ref_idx = np.nonzero(st.ref[b])[0]
         st.classified[b, ref_idx] = True
         larger = st.valid[b] & (st.scale_host[b].numpy() > 0.05)
         acc_e = np.nonzero(pred_np[b] & (tri_np[:, 0] < n) & (tri_np[:, 1] < n))[0]
         accepted = [st.tri_list[e] for e in acc_e]
-        new_ref = []
+        ref_before = st.ref[b].copy()
         for (i, j) in accepted:
-            i_ref, j_ref = i in ref_idx, j in ref_idx
-            if i_ref == j_ref:
-                continue
-            new_ref.append(j if i_ref else i)
-        for r in new_ref:
-            st.ref[b, r] = True
-        ref_now = [p for p in range(P) if st.ref[b, p]]
-        merge_list = []
-        for (i, j) in accepted:
-            if i in ref_now or j in ref_now:
-                continue
-            if st.ref[b, st.pivot[b][i]] or st.ref[b, st.pivot[b][j]]:
-                continue
-            merge_list.append((i, j))
+            if ref_before[i] != ref_before[j]:
+                st.ref[b, j if ref_before[i] else i] = True
+        ref_now = st.ref[b]
+        piv = st.pivot[b]
+        merge_list = [(i, j) for (i, j) in accepted
+                      if not (ref_now[i] or ref_now[j] or ref_now[piv[i]] or ref_now[piv[j]])]
         if bool((st.classified[b] == larger).all()):
             st.done[b] = True
             continue
         if merge and merge_list:
-            if posed is None:
-                posed = _posed_fragments(engine, st, x)
-            _merge_components(engine, st, b, merge_list, posed, x_host[b], noise)
+            G = st.graph[b]
+            G.add_edges_from(merge_list)
+            for comp in list(nx.connected_components(G)):
+                comp = list(comp)
+                members = [c for c in comp if st.node_valid[b][c]]
+                if len(members) <= 1:
+                    continue
+                pivot = max(comp, key=lambda c: st.scale_host[b, c])
+                comps.append((b, comp, members, pivot))
+                st.classified[b, comp] = True
         # the reference re-tests with the `larger_parts` computed before the merge (auto_aggl.py:288)
         if bool((st.classified[b] == larger).all()):
             st.done[b] = True
-    ref_dev.copy_(torch.as_tensor(st.ref).reshape(B * P).to(torch.uint8).to(dev))
+    if comps:
+        _merge_enqueue(engine, st, comps, x, x_host, noise)
+    ref_dev.copy_(engine.upload_array("ref_flags", st.ref.reshape(B * P).astype(np.uint8)))
 
 
-def _posed_fragments(engine, st, x):
+def _merge_enqueue(engine, st, comps, x, x_host, noise):
+    """auto_aggl.py:234-286 for every component in `comps` through pfpp_merge (asynchronous).  The host-side graph
+    state that does not depend on device results (pivots, validity) is updated here; init poses and the scale
+    mirror need the centroid / max-abs scale and are completed by _resolve_pending after the next download."""
     dev, P, B, N = engine.device, st.P, st.B, st.N
     nseg = B * P
-    seg_s = torch.arange(nseg, dtype=torch.int32, device=dev) * N
-    seg_l = torch.full((nseg,), N, dtype=torch.int32, device=dev)
-    seg_p = torch.arange(nseg, dtype=torch.int32, device=dev)
-    out = engine.buf("posed", (nseg, N, 3), torch.float32)
-    call("pfpp_pose_apply", st.part_pcs.data_ptr(), seg_s.data_ptr(), seg_l.data_ptr(), seg_p.data_ptr(), x.data_ptr(),
-         st.scale.data_ptr(), 1, nseg, out.data_ptr())
-    return out
-
-
-def _merge_components(engine, st, b, merge_list, posed, xb, noise):
-    """auto_aggl.py:234-286 for object b."""
-    dev, P, N = engine.device, st.P, st.N
-    G = st.graph[b]
-    G.add_edges_from(merge_list)
-    trans, rots = xb[:, :3], xb[:, 3:]
-    rot_m = quat_to_matrix(rots)
-    for comp in list(nx.connected_components(G)):
-        comp = list(comp)
-        if sum(st.node_valid[b][c] for c in comp) <= 1:
-            continue
-        pivot = max(comp, key=lambda c: st.scale_host[b, c])
-        members = [c for c in comp if st.node_valid[b][c]]
-        merged = torch.cat([posed[b * P + c] for c in members], 0)
-        centroid = merged.mean(dim=0)
-        merged = (merged - centroid).contiguous()
-        centroid_h = centroid.cpu()
+    ar = torch.arange(nseg, dtype=torch.int32, device=dev)
+    posed = engine.buf("posed", (nseg, N, 3), torch.float32)
+    # node_merge_utils.py:43-53 (normalised quaternion, clouds scaled by part_scale)
+    seg_start, seg_len = ar * N, torch.full_like(ar, N)  # named: both must stay alive until the launch is enqueued
+    call("pfpp_pose_apply", st.part_pcs.data_ptr(), seg_start.data_ptr(), seg_len.data_ptr(), ar.data_ptr(),
+         x.data_ptr(), st.scale.data_ptr(), 1, nseg, posed.data_ptr())
+    comp_start, member_slot, member_comp, pivot_slot, pair_i, pair_j = [0], [], [], [], [], []
+    seg_s, seg_l, seg_c, uniforms = [], [], [], []
+    rot_all = {}
+    for k, (b, comp, members, pivot) in enumerate(comps):
+        base = len(member_slot)
+        member_slot += [b * P + c for c in members]
+        member_comp += [k] * len(members)
+        comp_start.append(len(member_slot))
+        pivot_slot.append(b * P + pivot)
+        m = len(members)
+        ii, jj = np.nonzero(~np.eye(m, dtype=bool))
+        pair_i.append(base + ii)
+        pair_j.append(base + jj)
+        cs, abase = st.area_cs[b], st.area_base[b]
         for c in comp:
-            pv = st.pivot[b][c]
-            m = affine(rot_m[pv], trans[pv] - centroid_h)
-            st.init_pose[b][c] = m if st.init_pose[b][c] is None else m @ st.init_pose[b][c]
-        cs, base = st.area_cs[b], st.area_base[b]
-        for c in comp:
-            st.by_area[base + cs[c]:base + cs[c + 1]] = st.by_area_T[base + cs[c]:base + cs[c + 1]] - centroid
+            seg_s.append(abase + cs[c])
+            seg_l.append(cs[c + 1] - cs[c])
+            seg_c.append(k)
+        uniforms.append(noise.fps_uniform(b))
+        # host bookkeeping that needs no device result
+        if b not in rot_all:
+            rot_all[b] = quat_to_matrix(x_host[b][:, 3:])
+        pv = [st.pivot[b][c] for c in comp]
+        st.pending.append((b, comp, pivot, rot_all[b][pv].clone(), x_host[b][pv, :3].clone()))
         for c in comp:
             st.pivot[b][c] = pivot
-        ds = _remove_intersect_and_fps(engine, merged, len(members), N, noise, b)
-        mscale = ds.abs().max()
-        st.scale[b * P + pivot] = mscale
-        st.scale_host[b, pivot] = mscale.cpu()
-        st.part_pcs[b * P + pivot] = ds / mscale
-        for c in comp:
             st.valid[b, c] = False
             st.node_valid[b][c] = c == pivot
         st.valid[b, pivot] = True
-        st.classified[b, comp] = True
+    n_comp, n_clouds = len(comps), len(member_slot)
+    pair_i, pair_j = np.concatenate(pair_i), np.concatenate(pair_j)
+    n_pairs, n_segs = len(pair_i), len(seg_s)
+    tab = np.concatenate([comp_start, member_slot, member_comp, pivot_slot, pair_i, pair_j, seg_s, seg_l, seg_c]).astype(np.int32)
+    t = engine.upload_array("merge_tables", tab)
+    off = np.cumsum([0, n_comp + 1, n_clouds, n_clouds, n_comp, n_pairs, n_pairs, n_segs, n_segs])
+    ptr = [t.data_ptr() + 4 * int(o) for o in off]
+    u = torch.cat(uniforms).to(torch.float32).contiguous()
+    ws_bytes = int(_lib.load().pfpp_merge_workspace_bytes(n_clouds, n_comp, N))
+    ws = engine.buf("merge_ws", (ws_bytes,), torch.uint8)
+    result = torch.empty(n_comp, 8, dtype=torch.float32, device=dev)
+    call("pfpp_merge", posed.data_ptr(), N, n_comp, n_clouds, ptr[0], ptr[1], ptr[2], ptr[3], n_pairs, ptr[4], ptr[5],
+         u.data_ptr(), float(np.float32(0.001)), 20, n_segs, ptr[6], ptr[7], ptr[8], st.by_area_T.data_ptr(),
+         st.by_area.data_ptr(), st.part_pcs.data_ptr(), st.scale.data_ptr(), result.data_ptr(), ws.data_ptr(), ws_bytes)
+    st.pending_result = result
+    st._seg_key = None  # pivots changed
 
 
-def _remove_intersect_and_fps(engine, merged, n_clouds, N, noise, b):
-    """node_merge_utils.py:159-222 on device: normals + pairwise filter kernel, compaction, FPS to N."""
-    dev = engine.device
-    keep = torch.empty(n_clouds * N, dtype=torch.uint8, device=dev)
-    normals = torch.empty(n_clouds * N, 3, dtype=torch.float32, device=dev)
-    call("pfpp_merge_filter", merged.data_ptr(), n_clouds, N, 20, float(np.float32(0.001)), keep.data_ptr(),
-         normals.data_ptr())
-    pts = merged[keep.bool()].contiguous()
-    M = pts.shape[0]
-    ratio = torch.tensor(N / M, dtype=torch.float32)
-    n_out = int(torch.ceil(torch.tensor(float(M), dtype=torch.float32) * ratio))
-    start = noise.fps_start(b, M)
-    # [cloud_start, cloud_len, n_samples, start, out_start] -- kept alive until after the launch
-    meta = torch.as_tensor(np.asarray([0, M, n_out, start, 0], dtype=np.int32)).to(dev)
-    out_idx = torch.empty(n_out, dtype=torch.int32, device=dev)
-    dist = torch.empty(M, dtype=torch.float32, device=dev)
-    mp = meta.data_ptr()
-    call("pfpp_fps_ragged", pts.data_ptr(), mp, mp + 4, mp + 8, mp + 12, 1, dist.data_ptr(), mp + 16, out_idx.data_ptr())
-    return pts[out_idx.long()][:N]
+def _resolve_pending(st, result_host):
+    """Complete the host state of the merges enqueued by _merge_enqueue once their device results are on the host:
+    assign_init_pose (node_merge_utils.py:225-244) with the component centroid, scale mirror with max|ds|."""
+    if not st.pending:
+        return
+    N = st.N
+    for k, (b, comp, pivot, rot_m, trans) in enumerate(st.pending):
+        r = result_host[k]
+        if int(r[4]) < N:
+            raise _lib.PfppError(f"merge of object {b}: only {int(r[4])} points survive the intersection filter, fewer "
+                                 f"than the {N} the fragment slot holds (the reference fails on this shape as well)")
+        centroid = r[:3]
+        for c, rm, t in zip(comp, rot_m, trans):
+            m = affine(rm, t - centroid)
+            st.init_pose[b][c] = m if st.init_pose[b][c] is None else m @ st.init_pose[b][c]
+        st.scale_host[b, pivot] = r[3]
+    st.pending, st.pending_result = [], None

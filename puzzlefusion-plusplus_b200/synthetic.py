@@ -263,7 +263,7 @@ def make_encoder_state(seed=1, code_scale=0.35, use_asset=True):
     return sd
 
 
-def make_verifier_state(seed=2, C=256, layers=6, ff=2048, max_parts=MAX_PARTS):
+def make_verifier_state(seed=2, C=256, layers=6, ff=2048, max_parts=MAX_PARTS, accept_bias=3.1):
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for i in range(layers):
@@ -283,13 +283,15 @@ def make_verifier_state(seed=2, C=256, layers=6, ff=2048, max_parts=MAX_PARTS):
     # score around the 0.9 acceptance threshold, edges without matching points score below it.
     _linear(g, C, 7, sd, "edge_feature_emb", gain=4.0)
     _linear(g, 1, C, sd, "mlp_out", gain=4.0)
-    sd["mlp_out.bias"] = torch.tensor([3.1])
+    # accept_bias shifts every logit: lower values accept fewer edges per verify pass, so fewer parts are promoted to
+    # reference at once and more of them merge over several outer iterations (3.1 = the goldens' setting)
+    sd["mlp_out.bias"] = torch.tensor([float(accept_bias)])
     return sd
 
 
-def make_checkpoints(seed=0, max_parts=MAX_PARTS):
+def make_checkpoints(seed=0, max_parts=MAX_PARTS, accept_bias=3.1):
     return {
         "denoiser": make_denoiser_state(seed, max_parts=max_parts),
         "encoder": make_encoder_state(seed + 1),
-        "verifier": make_verifier_state(seed + 2, max_parts=max_parts),
+        "verifier": make_verifier_state(seed + 2, max_parts=max_parts, accept_bias=accept_bias),
     }
