@@ -90,8 +90,10 @@ int pfpp_vq(const void* z, int z_is_bf16, long long n_chunks, const float* codeb
  * (utils/pn2_utils.py:139-148,209-214) fused in one tcgen05 kernel; activations stay in shared
  * memory / TMEM.  level in {1,2,3} selects (nsample, D, C1, C2, C3) = (32,0,64,64,128),
  * (64,128,128,128,256), (64,256,256,256,512).  feats [K,N,D] bf16.  Layer 0 is split: w0_feat [C1, D]
- * bf16 (feature columns, tensor cores; NULL for level 1) and w0_xyz [C1, 4] fp32 (dx,dy,dz columns, applied
- * as fp32 FMAs in the epilogue); w1 [C2,C1], w2 [C3,C2] bf16; all with BatchNorm folded; out [K*S, C3] bf16. */
+ * bf16 (feature columns; NULL for level 1) and w0_xyz [C1, 4] fp32 (dx,dy,dz columns: the kernel splits weights
+ * and centroid offsets into bf16 hi/lo pairs and applies them as ONE extra K=16 tcgen05 step,
+ * w d = w_hi d_hi + w_hi d_lo + w_lo d_hi, 2^-16 relative); w1 [C2,C1], w2 [C3,C2] bf16; all with BatchNorm folded;
+ * out [K*S, C3] bf16. */
 int pfpp_sa_fused(int level, const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K, int N,
                   int S, const void* w0_feat, const float* w0_xyz, const float* b0, const void* w1, const float* b1,
                   const void* w2, const float* b2, void* out, cudaStream_t stream);
@@ -115,6 +117,24 @@ int pfpp_gemm_f32(const float* A, int lda, const float* W, int ldw, const float*
  * tensor maps are encoded per call on the host (driver entry point resolved at first use). */
 int pfpp_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* residual, int ldr,
                    void* C, int ldc, int c_bf16, int M, int N, int K, int epilogue, cudaStream_t stream);
+
+/* fp32-grade contraction on the tensor cores ("bf16x3"): operands in the bf16 hi/lo SPLIT format -- a row of a
+ * split tensor holds ld elements, the hi half bf16(v) at columns [0, ld/2) and the lo half bf16(v - hi) at
+ * [ld/2, ld) -- and three tcgen05 passes A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T into one fp32 TMEM accumulator
+ * (relative error ~2^-16 per product; the reference's fp32 nn.Linear / conv1x1, same call sites as pfpp_gemm_f32).
+ * A [M, lda >= 2K], W [N, ldw >= 2K] split; K multiple of 8, lda / ldw multiples of 16.  C is fp32 [M, ldc]
+ * (c_split = 0; residual fp32, may alias C) or split [M, ldc] (c_split = 1: the operand of the next layer).
+ * GELU / GEGLU epilogues use the exact erf form. */
+int pfpp_gemm_bf16x3(const void* A, int lda, const void* W, int ldw, const float* bias, const float* residual, int ldr,
+                     void* C, int ldc, int c_split, int M, int N, int K, int epilogue, cudaStream_t stream);
+
+/* fp32 [rows, C] (leading dimension ldx) -> split bf16 [rows, ldo] (hi at c, lo at ldo/2 + c, zero padding). */
+int pfpp_split_bf16(const float* x, long long rows, int C, int ldx, void* out, int ldo, cudaStream_t stream);
+
+/* Output-format flag of the kernels below and of pfpp_group_gather / pfpp_group_max (`out_bf16`, `is_bf16`,
+ * `io_bf16`): 0 = fp32, 1 = bf16, 2 = bf16 hi/lo split rows (ld counts BOTH halves).  pfpp_group_gather(2): feats are
+ * split [K,N,2D], out rows hold 2*ld elements; pfpp_group_max(2): fp32 in, split out; pfpp_attention_varlen(2): fp32
+ * q/k/v in, split out. */
 
 /* ---- denoiser tokens -------------------------------------------------------------------- */
 
@@ -228,6 +248,17 @@ int pfpp_merge(const float* posed, int n_points, int n_comp, int n_clouds, const
 /* chamferdist / pytorch3d knn_points(K=1) squared distances for the evaluation metrics
  * (denoiser/evaluation/evaluator.py:108,137): out[b,i] = min_j |a[b,i] - b[b,j]|^2. */
 int pfpp_nn_sqdist(const float* a, const float* b, int batches, int N, int M, float* out, cudaStream_t stream);
+
+/* ---- Chamfer distance with gradients ----------------------------------- */
+
+/* chamfer_cuda.chamfer_forward (Jigsaw_matching/utils/chamfer/cuda/chamfer_kernel.cu:31-173): nearest neighbour of
+ * every point of xyz1 [B,n1,3] in xyz2 [B,n2,3] and vice versa: squared distances and the FIRST minimising index. */
+int pfpp_chamfer_forward(const float* xyz1, const float* xyz2, int batches, int n1, int n2, float* dist1, int* idx1,
+                         float* dist2, int* idx2, cudaStream_t stream);
+/* chamfer_cuda.chamfer_backward (chamfer_kernel.cu:175-260): grad_xyz1 [B,n1,3], grad_xyz2 [B,n2,3] (zeroed here). */
+int pfpp_chamfer_backward(const float* grad_dist1, const float* grad_dist2, const float* xyz1, const float* xyz2,
+                          const int* idx1, const int* idx2, int batches, int n1, int n2, float* grad_xyz1,
+                          float* grad_xyz2, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,8 @@ SIGNATURES = {
     "pfpp_vq": [_P, _I, _L, _P, _I, _P, _P, _P],
     "pfpp_gemm_f32": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "pfpp_gemm_bf16": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pfpp_gemm_bf16x3": [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "pfpp_split_bf16": [_P, _L, _I, _I, _P, _I, _P],
     "pfpp_embed_features": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P],
     "pfpp_combine_embed": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "pfpp_layernorm": [_P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _P, _P, _P],
@@ -50,6 +52,8 @@ SIGNATURES = {
     "pfpp_verifier_head": [_P, _P, _I, _P, _P, _I, _P, _P],
     "pfpp_merge_filter": [_P, _I, _I, _I, _F, _P, _P, _P],
     "pfpp_nn_sqdist": [_P, _P, _I, _I, _I, _P, _P],
+    "pfpp_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "pfpp_chamfer_backward": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
     "pfpp_merge": [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                    ctypes.c_size_t, _P],
 }

@@ -112,11 +112,28 @@ __device__ __forceinline__ float tc_act(float v) {
   return v;
 }
 
-template <int EPI, bool OUT_BF16>
+// OUT selects the output format of every kernel below: 0 = fp32, 1 = bf16, 2 = bf16 hi/lo SPLIT (the fp32 value v is
+// stored as hi = bf16(v) at column c and lo = bf16(v - hi) at column c + lo_off of the same row: the operand format
+// of the fp32-grade "bf16x3" contraction).  `parts` = 1: plain bf16 GEMM; 3: split operands, the K loop runs three
+// times over (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) into the same fp32 accumulator (map_a2 / map_b2 address the lo
+// halves): a*w = a_hi w_hi + a_lo w_hi + a_hi w_lo + O(2^-16 |a w|), every product exact in the fp32 accumulator.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<uint32_t*>(&h), lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+template <int EPI, int OUT>
+__device__ __forceinline__ void epilogue_store(const uint32_t* v, int row, int nb, int M, int N, const float* __restrict__ bias,
+                                               const float* residual, int ldr, void* Cout, int ldc, int lo_off);
+
+template <int EPI, int OUT>
 __global__ void __launch_bounds__(128)
     gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                        const float* __restrict__ bias, const float* residual, int ldr, void* Cout, int ldc, int M,
-                        int N, int K) {
+                        const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2, int parts,
+                        const float* __restrict__ bias, const float* residual, int ldr, void* Cout, int ldc, int lo_off,
+                        int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
@@ -128,7 +145,8 @@ __global__ void __launch_bounds__(128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
-  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int kb_part = (K + TC_BK - 1) / TC_BK;
+  const int num_kb = kb_part * parts;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -152,12 +170,13 @@ __global__ void __launch_bounds__(128)
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % TC_STAGES;
       const uint32_t round = kb / TC_STAGES;
+      const int part = kb / kb_part, kk = kb - part * kb_part;
       mbar_wait(bar_base + 8 * (TC_STAGES + s), (round & 1) ^ 1);  // slot free (passes immediately in round 0)
       const uint32_t full = bar_base + 8 * s;
       mbar_expect_tx(full, TC_STAGE_BYTES);
       const uint32_t sa = smem_base + s * TC_STAGE_BYTES;
-      tma_load_2d(sa, &map_a, full, kb * TC_BK, m0);
-      tma_load_2d(sa + TC_A_BYTES, &map_b, full, kb * TC_BK, n0);
+      tma_load_2d(sa, part == 1 ? &map_a2 : &map_a, full, kk * TC_BK, m0);
+      tma_load_2d(sa + TC_A_BYTES, part == 2 ? &map_b2 : &map_b, full, kk * TC_BK, n0);
     }
   } else if (warp == 1 && lane == 0) {
     // ---- MMA issuer ----
@@ -188,88 +207,7 @@ __global__ void __launch_bounds__(128)
     uint32_t v[32];
     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    const int nb = n0 + c * 32;
-    if (row < M && nb < N) {
-      if (EPI == PFPP_EPI_GEGLU) {
-        // interleaved (value, gate) column pairs -> 16 outputs at columns nb/2 .. nb/2+15
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const int n = nb + j;
-          float val = __uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f);
-          float gate = __uint_as_float(v[j + 1]) + ((bias && n + 1 < N) ? bias[n + 1] : 0.f);
-          o[j >> 1] = val * (OUT_BF16 ? gelu_tanh_fast(gate) : gelu_erf(gate));
-        }
-        const size_t off = (size_t)row * ldc + (nb >> 1);
-        if (nb + 32 <= N && OUT_BF16 && (ldc % 8) == 0) {
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + off;
-#pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
-            pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(cp + j) = pk;
-          }
-        } else {
-          for (int j = 0; j < 16; ++j) {
-            if (nb + 2 * j + 1 < N) {
-              if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(Cout)[off + j] = __float2bfloat16_rn(o[j]);
-              else reinterpret_cast<float*>(Cout)[off + j] = o[j];
-            }
-          }
-        }
-      } else {
-        float o[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          int n = nb + j;
-          float t = __uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f);
-          o[j] = tc_act<EPI>(t);
-        }
-        if (residual) {
-          const float* rp = residual + (size_t)row * ldr + nb;
-          if (nb + 32 <= N && (ldr % 4) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-              o[j] += r4.x, o[j + 1] += r4.y, o[j + 2] += r4.z, o[j + 3] += r4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < N) o[j] += rp[j];
-          }
-        }
-        if (OUT_BF16) {
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * ldc + nb;
-          if (nb + 32 <= N && (ldc % 8) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(cp + j) = pk;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < N) cp[j] = __float2bfloat16_rn(o[j]);
-          }
-        } else {
-          float* cp = reinterpret_cast<float*>(Cout) + (size_t)row * ldc + nb;
-          if (nb + 32 <= N && (ldc % 4) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < N) cp[j] = o[j];
-          }
-        }
-      }
-    }
+    epilogue_store<EPI, OUT>(v, row, n0 + c * 32, M, N, bias, residual, ldr, Cout, ldc, lo_off);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -285,10 +223,10 @@ __global__ void __launch_bounds__(128)
 // XOR-swizzled by row, conflict-free both ways) so that in the second phase 8 consecutive lanes cover one
 // 128-byte row segment: every global load (residual) and store is a fully coalesced line segment.  Bias,
 // activation / GEGLU and the fp32 residual add happen in the second phase on 4 consecutive columns per lane.
-template <int EPI, bool OUT_BF16>
+template <int EPI, int OUT>
 __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t* v, float* stage, int lane, int row0, int nb,
                                                          int M, int N, const float* __restrict__ bias,
-                                                         const float* residual, int ldr, void* Cout, int ldc) {
+                                                         const float* residual, int ldr, void* Cout, int ldc, int lo_off) {
   // phase 1: thread = row `lane` of the chunk; 8 x 16-byte chunks, chunk j stored at slot j ^ (lane & 7)
   uint4* srow = reinterpret_cast<uint4*>(stage) + lane * 8;
 #pragma unroll
@@ -324,10 +262,22 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t* v, floa
                   __uint_as_float(raw.w) + b4[3]};
     if (EPI == PFPP_EPI_GEGLU) {
       // interleaved (value, gate) pairs: columns (n, n+1) -> output column n/2, (n+2, n+3) -> n/2 + 1
-      const float o0 = a[0] * (OUT_BF16 ? gelu_tanh_fast(a[1]) : gelu_erf(a[1]));
-      const float o1 = a[2] * (OUT_BF16 ? gelu_tanh_fast(a[3]) : gelu_erf(a[3]));
+      const float o0 = a[0] * (OUT == 1 ? gelu_tanh_fast(a[1]) : gelu_erf(a[1]));
+      const float o1 = a[2] * (OUT == 1 ? gelu_tanh_fast(a[3]) : gelu_erf(a[3]));
       const size_t off = (size_t)row * ldc + (n >> 1);
-      if (OUT_BF16) {
+      if (OUT == 2) {
+        uint32_t hi, lo;
+        split2(o0, o1, hi, lo);
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + off;
+        if (n + 3 < N && (ldc % 2) == 0 && (lo_off % 2) == 0) {
+          *reinterpret_cast<uint32_t*>(cp) = hi;
+          *reinterpret_cast<uint32_t*>(cp + lo_off) = lo;
+        } else {
+          const __nv_bfloat162 h2 = *reinterpret_cast<__nv_bfloat162*>(&hi), l2 = *reinterpret_cast<__nv_bfloat162*>(&lo);
+          if (n + 1 < N) cp[0] = h2.x, cp[lo_off] = l2.x;
+          if (n + 3 < N) cp[1] = h2.y, cp[lo_off + 1] = l2.y;
+        }
+      } else if (OUT == 1) {
         if (n + 3 < N && (ldc % 2) == 0) {
           __nv_bfloat162 p = __floats2bfloat162_rn(o0, o1);
           *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(Cout) + off) = p;
@@ -351,7 +301,21 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t* v, floa
       for (int j = 0; j < 4; ++j)
         if (n + j < N) a[j] += rp[j];
     }
-    if (OUT_BF16) {
+    if (OUT == 2) {
+      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * ldc + n;
+      uint2 hi, lo;
+      split2(a[0], a[1], hi.x, lo.x);
+      split2(a[2], a[3], hi.y, lo.y);
+      if (full && (ldc % 4) == 0 && (lo_off % 4) == 0) {
+        *reinterpret_cast<uint2*>(cp) = hi;
+        *reinterpret_cast<uint2*>(cp + lo_off) = lo;
+      } else {
+        const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hi);
+        const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&lo);
+        for (int j = 0; j < 4; ++j)
+          if (n + j < N) cp[j] = hp[j], cp[lo_off + j] = lp[j];
+      }
+    } else if (OUT == 1) {
       __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * ldc + n;
       if (full && (ldc % 4) == 0) {
         __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]), p1 = __floats2bfloat162_rn(a[2], a[3]);
@@ -434,84 +398,82 @@ __device__ __forceinline__ void epilogue_slab_tma(uint32_t taddr, int acc_col0, 
 }
 
 // Shared epilogue for one 32-column chunk of one accumulator row (values v[32] straight from tcgen05.ld).
-template <int EPI, bool OUT_BF16>
+template <int EPI, int OUT>
 __device__ __forceinline__ void epilogue_store(const uint32_t* v, int row, int nb, int M, int N, const float* __restrict__ bias,
-                                               const float* residual, int ldr, void* Cout, int ldc) {
+                                               const float* residual, int ldr, void* Cout, int ldc, int lo_off) {
   if (!(row < M && nb < N)) return;
+  float o[32];
+  int n_out, col0;  // number of output values of this chunk and their first output column
   if (EPI == PFPP_EPI_GEGLU) {
-    float o[16];
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       const int n = nb + j;
       float val = __uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f);
       float gate = __uint_as_float(v[j + 1]) + ((bias && n + 1 < N) ? bias[n + 1] : 0.f);
-      o[j >> 1] = val * (OUT_BF16 ? gelu_tanh_fast(gate) : gelu_erf(gate));
+      o[j >> 1] = val * (OUT == 1 ? gelu_tanh_fast(gate) : gelu_erf(gate));
     }
-    const size_t off = (size_t)row * ldc + (nb >> 1);
-    if (nb + 32 <= N && OUT_BF16 && (ldc % 8) == 0) {
-      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + off;
+    n_out = (N - nb) / 2 < 16 ? (N - nb) / 2 : 16;
+    col0 = nb >> 1;
+  } else {
 #pragma unroll
-      for (int j = 0; j < 16; j += 8) {
-        uint4 pk;
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-        pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
-        pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
-        *reinterpret_cast<uint4*>(cp + j) = pk;
-      }
-    } else {
-      for (int j = 0; j < 16; ++j) {
-        if (nb + 2 * j + 1 < N) {
-          if (OUT_BF16) reinterpret_cast<__nv_bfloat16*>(Cout)[off + j] = __float2bfloat16_rn(o[j]);
-          else reinterpret_cast<float*>(Cout)[off + j] = o[j];
+    for (int j = 0; j < 32; ++j) {
+      const int n = nb + j;
+      o[j] = tc_act<EPI>(__uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f));
+    }
+    if (residual) {
+      const float* rp = residual + (size_t)row * ldr + nb;
+      if (nb + 32 <= N && (ldr % 4) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+          o[j] += r4.x, o[j + 1] += r4.y, o[j + 2] += r4.z, o[j + 3] += r4.w;
         }
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < N) o[j] += rp[j];
       }
+    }
+    n_out = N - nb < 32 ? N - nb : 32;
+    col0 = nb;
+  }
+  constexpr int NV = EPI == PFPP_EPI_GEGLU ? 16 : 32;
+  const size_t off = (size_t)row * ldc + col0;
+  if (OUT == 0) {
+    float* cp = reinterpret_cast<float*>(Cout) + off;
+    if (n_out == NV && (ldc % 4) == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    } else {
+      for (int j = 0; j < NV; ++j)
+        if (j < n_out) cp[j] = o[j];
     }
     return;
   }
-  float o[32];
+  __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + off;
+  const bool vec = n_out == NV && (ldc % 8) == 0 && (OUT == 1 || (lo_off % 8) == 0);
+  if (vec) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int n = nb + j;
-    o[j] = tc_act<EPI>(__uint_as_float(v[j]) + ((bias && n < N) ? bias[n] : 0.f));
-  }
-  if (residual) {
-    const float* rp = residual + (size_t)row * ldr + nb;
-    if (nb + 32 <= N && (ldr % 4) == 0) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-        o[j] += r4.x, o[j + 1] += r4.y, o[j + 2] += r4.z, o[j + 3] += r4.w;
-      }
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (nb + j < N) o[j] += rp[j];
-    }
-  }
-  if (OUT_BF16) {
-    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * ldc + nb;
-    if (nb + 32 <= N && (ldc % 8) == 0) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 pk;
+    for (int j = 0; j < NV; j += 8) {
+      uint4 hi, lo;
+      if (OUT == 2) {
+        split2(o[j], o[j + 1], hi.x, lo.x), split2(o[j + 2], o[j + 3], hi.y, lo.y);
+        split2(o[j + 4], o[j + 5], hi.z, lo.z), split2(o[j + 6], o[j + 7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(cp + lo_off + j) = lo;
+      } else {
         __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
         __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-        pk.x = *reinterpret_cast<uint32_t*>(&p0), pk.y = *reinterpret_cast<uint32_t*>(&p1);
-        pk.z = *reinterpret_cast<uint32_t*>(&p2), pk.w = *reinterpret_cast<uint32_t*>(&p3);
-        *reinterpret_cast<uint4*>(cp + j) = pk;
+        hi.x = *reinterpret_cast<uint32_t*>(&p0), hi.y = *reinterpret_cast<uint32_t*>(&p1);
+        hi.z = *reinterpret_cast<uint32_t*>(&p2), hi.w = *reinterpret_cast<uint32_t*>(&p3);
       }
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (nb + j < N) cp[j] = __float2bfloat16_rn(o[j]);
+      *reinterpret_cast<uint4*>(cp + j) = hi;
     }
   } else {
-    float* cp = reinterpret_cast<float*>(Cout) + (size_t)row * ldc + nb;
-    if (nb + 32 <= N && (ldc % 4) == 0) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (nb + j < N) cp[j] = o[j];
+    for (int j = 0; j < NV; ++j) {
+      if (j < n_out) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(o[j]);
+        cp[j] = h;
+        if (OUT == 2) cp[lo_off + j] = __float2bfloat16_rn(o[j] - __bfloat162float(h));
+      }
     }
   }
 }
@@ -674,8 +636,8 @@ __global__ void __launch_bounds__(T2_THREADS)
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        epilogue_chunk_coalesced<EPI, OUT_BF16>(v, stage, lane, m0 + q * 32, n0 + c * 32, m_store, N, bias, residual, ldr,
-                                                Cout, ldc);
+        epilogue_chunk_coalesced<EPI, OUT_BF16 ? 1 : 0>(v, stage, lane, m0 + q * 32, n0 + c * 32, m_store, N, bias, residual,
+                                                        ldr, Cout, ldc, 0);
       }
       // this warp is done with the accumulator buffer: hand it back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -743,11 +705,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
       : "memory");
 }
 
-template <int EPI, bool OUT_BF16>
+template <int EPI, int OUT>
 __global__ void __launch_bounds__(T2_THREADS)
     gemm_bf16_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2, int parts,
                          const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, const float* residual,
-                         int ldr, void* Cout, int ldc, int M, int N, int K) {
+                         int ldr, void* Cout, int ldc, int lo_off, int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_stage = smem_base + T3_STAGES * T3_STAGE_BYTES;
@@ -762,7 +725,8 @@ __global__ void __launch_bounds__(T2_THREADS)
   const bool leader = crank == 0;
   const int tiles_n = (N + 255) / 256, tiles_mp = (M + 255) / 256;
   const int num_items = tiles_mp * tiles_n;
-  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int kb_part = (K + TC_BK - 1) / TC_BK;
+  const int num_kb = kb_part * parts;  // parts = 3: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) into one accumulator
   const int worker = (int)(blockIdx.x >> 1), n_workers = (int)(gridDim.x >> 1);
 
   if (threadIdx.x == 0) {
@@ -797,8 +761,9 @@ __global__ void __launch_bounds__(T2_THREADS)
           const uint32_t lead_full = (bar_full + 8 * s) & PEER_BIT_MASK;
           if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * T3_STAGE_BYTES);  // both CTAs' halves
           const uint32_t sa = smem_base + s * T3_STAGE_BYTES;
-          tma_load_2d_2sm(sa, &map_a, lead_full, kb * TC_BK, m0);
-          tma_load_2d_2sm(sa + T3_HALF_BYTES, &map_b, lead_full, kb * TC_BK, n0);
+          const int part = kb / kb_part, kk = kb - part * kb_part;
+          tma_load_2d_2sm(sa, part == 1 ? &map_a2 : &map_a, lead_full, kk * TC_BK, m0);
+          tma_load_2d_2sm(sa + T3_HALF_BYTES, part == 2 ? &map_b2 : &map_b, lead_full, kk * TC_BK, n0);
         }
       }
     }
@@ -834,7 +799,7 @@ __global__ void __launch_bounds__(T2_THREADS)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
       float* stage = reinterpret_cast<float*>(smem_raw + (epi_stage - smem_u32(smem_raw)) + (warp - 2) * 4096);
-      if (OUT_BF16 && residual == nullptr) {
+      if (OUT == 1 && residual == nullptr) {
         // bf16 outputs (QKV, GEGLU hidden): shared-memory box + TMA store, 64 output columns per box
         const uint32_t stage_addr = epi_stage + (warp - 2) * 4096;
         if (EPI == PFPP_EPI_GEGLU) {
@@ -859,8 +824,8 @@ __global__ void __launch_bounds__(T2_THREADS)
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        epilogue_chunk_coalesced<EPI, OUT_BF16>(v, stage, lane, m0 + q * 32, n0 + c * 32, M, N, bias, residual, ldr, Cout,
-                                                ldc);
+        epilogue_chunk_coalesced<EPI, OUT>(v, stage, lane, m0 + q * 32, n0 + c * 32, M, N, bias, residual, ldr, Cout, ldc,
+                                           lo_off);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -870,7 +835,7 @@ __global__ void __launch_bounds__(T2_THREADS)
       }
     }
   }
-  if (OUT_BF16 && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // TMA stores done
+  if (OUT == 1 && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // TMA stores done
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync_all();
@@ -958,12 +923,17 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, 
                 : launch_tc2_impl<EPI, false, false>(ma, mb, bias, residual, ldr, C, ldc, M, N, K, stream);
 }
 
-template <int EPI, bool OUT_BF16>
-int launch_tc3_impl(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* residual, int ldr,
-                    void* C, int ldc, int M, int N, int K, cudaStream_t stream) {
-  auto kern = gemm_bf16_tc3_kernel<EPI, OUT_BF16>;
-  CUtensorMap mc = ma;  // placeholder when the TMA-store path is not taken
-  if (OUT_BF16 && residual == nullptr) {
+struct GemmMaps {
+  CUtensorMap a, b, a2, b2;
+  int parts;
+};
+
+template <int EPI, int OUT>
+int launch_tc3_impl(const GemmMaps& m, const float* bias, const float* residual, int ldr, void* C, int ldc, int lo_off,
+                    int M, int N, int K, cudaStream_t stream) {
+  auto kern = gemm_bf16_tc3_kernel<EPI, OUT>;
+  CUtensorMap mc = m.a;  // placeholder when the TMA-store path is not taken
+  if (OUT == 1 && residual == nullptr) {
     // output boxes of [32 rows x 64 bf16], 128B-swizzled like the staging tile
     auto fn = get_encode_fn();
     if (!fn) return PFPP_EUNSUPPORTED;
@@ -990,30 +960,80 @@ int launch_tc3_impl(const CUtensorMap& ma, const CUtensorMap& mb, const float* b
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, bias, residual, ldr, C, ldc, M, N, K);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.a2, m.b2, m.parts, mc, bias, residual, ldr, C, ldc, lo_off, M,
+                                     N, K);
   if (e != cudaSuccess) return (int)e;
   PFPP_RETURN_LAST();
 }
 
 template <int EPI>
-int launch_tc3(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* residual, int ldr, void* C,
-               int ldc, int c_bf16, int M, int N, int K, cudaStream_t stream) {
-  return c_bf16 ? launch_tc3_impl<EPI, true>(ma, mb, bias, residual, ldr, C, ldc, M, N, K, stream)
-                : launch_tc3_impl<EPI, false>(ma, mb, bias, residual, ldr, C, ldc, M, N, K, stream);
+int launch_tc3(const GemmMaps& m, const float* bias, const float* residual, int ldr, void* C, int ldc, int lo_off, int out,
+               int M, int N, int K, cudaStream_t stream) {
+  if (out == 2) return launch_tc3_impl<EPI, 2>(m, bias, residual, ldr, C, ldc, lo_off, M, N, K, stream);
+  return out ? launch_tc3_impl<EPI, 1>(m, bias, residual, ldr, C, ldc, lo_off, M, N, K, stream)
+             : launch_tc3_impl<EPI, 0>(m, bias, residual, ldr, C, ldc, lo_off, M, N, K, stream);
+}
+
+template <int EPI, int OUT>
+int launch_tc_impl(const GemmMaps& m, const float* bias, const float* residual, int ldr, void* C, int ldc, int lo_off, int M,
+                   int N, int K, cudaStream_t stream) {
+  dim3 grid(pfpp_cdiv(N, TC_BN), pfpp_cdiv(M, TC_BM));
+  PFPP_ENSURE_SMEM((gemm_bf16_tc_kernel<EPI, OUT>), TC_SMEM_BYTES);
+  gemm_bf16_tc_kernel<EPI, OUT><<<grid, 128, TC_SMEM_BYTES, stream>>>(m.a, m.b, m.a2, m.b2, m.parts, bias, residual, ldr, C,
+                                                                      ldc, lo_off, M, N, K);
+  PFPP_RETURN_LAST();
 }
 
 template <int EPI>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* residual, int ldr, void* C,
-              int ldc, int c_bf16, int M, int N, int K, cudaStream_t stream) {
-  dim3 grid(pfpp_cdiv(N, TC_BN), pfpp_cdiv(M, TC_BM));
-  if (c_bf16) {
-    PFPP_ENSURE_SMEM((gemm_bf16_tc_kernel<EPI, true>), TC_SMEM_BYTES);
-    gemm_bf16_tc_kernel<EPI, true><<<grid, 128, TC_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
-  } else {
-    PFPP_ENSURE_SMEM((gemm_bf16_tc_kernel<EPI, false>), TC_SMEM_BYTES);
-    gemm_bf16_tc_kernel<EPI, false><<<grid, 128, TC_SMEM_BYTES, stream>>>(ma, mb, bias, residual, ldr, C, ldc, M, N, K);
+int launch_tc(const GemmMaps& m, const float* bias, const float* residual, int ldr, void* C, int ldc, int lo_off, int out,
+              int M, int N, int K, cudaStream_t stream) {
+  if (out == 2) return launch_tc_impl<EPI, 2>(m, bias, residual, ldr, C, ldc, lo_off, M, N, K, stream);
+  return out ? launch_tc_impl<EPI, 1>(m, bias, residual, ldr, C, ldc, lo_off, M, N, K, stream)
+             : launch_tc_impl<EPI, 0>(m, bias, residual, ldr, C, ldc, lo_off, M, N, K, stream);
+}
+
+// out: 0 fp32, 1 bf16, 2 bf16 hi/lo split.  A_lo / W_lo != nullptr: split operands (3 passes over K).
+int gemm_dispatch(const void* A, const void* A_lo, int lda, const void* W, const void* W_lo, int ldw, const float* bias,
+                  const float* residual, int ldr, void* C, int ldc, int lo_off, int out, int M, int N, int K,
+                  int epilogue, cudaStream_t stream) {
+  GemmMaps m;
+  m.parts = (A_lo && W_lo) ? 3 : 1;
+  int rc = make_map(&m.a, A, M, K, lda, TC_BM);
+  if (rc) return rc;
+  static const int v2_mode = []() {
+    // 0 = 128x128 kernel only, 1 = persistent 128x256, 2 = + cluster multicast of W, 3 = CTA-pair (cta_group::2)
+    const char* e = getenv("PFPP_GEMM_V2");
+    return e ? atoi(e) : 3;
+  }();
+  const bool wide = N >= T2_BN && M >= 2 * TC_BM && v2_mode != 0;  // persistent 128x256 kernel for the wide projections
+  const bool mc = wide && v2_mode == 2 && (N % T2_BN) == 0 && m.parts == 1 && out != 2;
+  const bool pair = wide && (v2_mode >= 3 || m.parts == 3 || out == 2) &&
+                    (out != 1 || (ldc % 8) == 0);  // cta_group::2 kernel (bf16 C through TMA stores)
+  const int box_b = wide ? ((mc || pair) ? T2_BN / 2 : T2_BN) : TC_BN;
+  rc = make_map(&m.b, W, N, K, ldw, box_b);
+  if (rc) return rc;
+  m.a2 = m.a, m.b2 = m.b;
+  if (m.parts == 3) {
+    rc = make_map(&m.a2, A_lo, M, K, lda, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&m.b2, W_lo, N, K, ldw, box_b);
+    if (rc) return rc;
   }
-  PFPP_RETURN_LAST();
+#define PFPP_EPI_SWITCH(FN, ...)                                    \
+  switch (epilogue) {                                               \
+    case PFPP_EPI_NONE: return FN<PFPP_EPI_NONE>(__VA_ARGS__);      \
+    case PFPP_EPI_RELU: return FN<PFPP_EPI_RELU>(__VA_ARGS__);      \
+    case PFPP_EPI_GELU: return FN<PFPP_EPI_GELU>(__VA_ARGS__);      \
+    case PFPP_EPI_SILU: return FN<PFPP_EPI_SILU>(__VA_ARGS__);      \
+    case PFPP_EPI_GEGLU: return FN<PFPP_EPI_GEGLU>(__VA_ARGS__);    \
+    default: return PFPP_EINVAL;                                    \
+  }
+  if (pair) { PFPP_EPI_SWITCH(launch_tc3, m, bias, residual, ldr, C, ldc, lo_off, out, M, N, K, stream) }
+  if (wide && m.parts == 1 && out != 2) {
+    PFPP_EPI_SWITCH(launch_tc2, m.a, m.b, bias, residual, ldr, C, ldc, out, M, N, K, mc, stream)
+  }
+  PFPP_EPI_SWITCH(launch_tc, m, bias, residual, ldr, C, ldc, lo_off, out, M, N, K, stream)
+#undef PFPP_EPI_SWITCH
 }
 
 }  // namespace
@@ -1027,63 +1047,20 @@ extern "C" int pfpp_gemm_bf16(const void* A, int lda, const void* W, int ldw, co
   PFPP_CHECK_ARG((K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0);
   PFPP_CHECK_ARG((((uintptr_t)A) & 15) == 0 && (((uintptr_t)W) & 15) == 0);
   if (M == 0) return PFPP_OK;
-  CUtensorMap ma, mb;
-  int rc = make_map(&ma, A, M, K, lda, TC_BM);
-  if (rc) return rc;
-  static const int v2_mode = []() {
-    // 0 = 128x128 kernel only, 1 = persistent 128x256, 2 = + cluster multicast of W, 3 = CTA-pair (cta_group::2)
-    const char* e = getenv("PFPP_GEMM_V2");
-    return e ? atoi(e) : 3;
-  }();
-  const bool wide = N >= T2_BN && M >= 2 * TC_BM && v2_mode != 0;  // persistent 128x256 kernel for the wide projections
-  const bool mc = wide && v2_mode == 2 && (N % T2_BN) == 0;
-  const bool pair = wide && v2_mode >= 3 && (!c_bf16 || (ldc % 8) == 0);  // cta_group::2 kernel (bf16 C through TMA stores)
-  rc = make_map(&mb, W, N, K, ldw, wide ? ((mc || pair) ? T2_BN / 2 : T2_BN) : TC_BN);
-  if (rc) return rc;
-  if (pair) {
-    switch (epilogue) {
-      case PFPP_EPI_NONE:
-        return launch_tc3<PFPP_EPI_NONE>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-      case PFPP_EPI_RELU:
-        return launch_tc3<PFPP_EPI_RELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-      case PFPP_EPI_GELU:
-        return launch_tc3<PFPP_EPI_GELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-      case PFPP_EPI_SILU:
-        return launch_tc3<PFPP_EPI_SILU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-      case PFPP_EPI_GEGLU:
-        return launch_tc3<PFPP_EPI_GEGLU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-      default:
-        return PFPP_EINVAL;
-    }
-  }
-  if (wide) {
-    switch (epilogue) {
-      case PFPP_EPI_NONE:
-        return launch_tc2<PFPP_EPI_NONE>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
-      case PFPP_EPI_RELU:
-        return launch_tc2<PFPP_EPI_RELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
-      case PFPP_EPI_GELU:
-        return launch_tc2<PFPP_EPI_GELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
-      case PFPP_EPI_SILU:
-        return launch_tc2<PFPP_EPI_SILU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
-      case PFPP_EPI_GEGLU:
-        return launch_tc2<PFPP_EPI_GEGLU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, mc, stream);
-      default:
-        return PFPP_EINVAL;
-    }
-  }
-  switch (epilogue) {
-    case PFPP_EPI_NONE:
-      return launch_tc<PFPP_EPI_NONE>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-    case PFPP_EPI_RELU:
-      return launch_tc<PFPP_EPI_RELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-    case PFPP_EPI_GELU:
-      return launch_tc<PFPP_EPI_GELU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-    case PFPP_EPI_SILU:
-      return launch_tc<PFPP_EPI_SILU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-    case PFPP_EPI_GEGLU:
-      return launch_tc<PFPP_EPI_GEGLU>(ma, mb, bias, residual, ldr, C, ldc, c_bf16, M, N, K, stream);
-    default:
-      return PFPP_EINVAL;
-  }
+  return gemm_dispatch(A, nullptr, lda, W, nullptr, ldw, bias, residual, ldr, C, ldc, 0, c_bf16 ? 1 : 0, M, N, K, epilogue,
+                       stream);
+}
+
+extern "C" int pfpp_gemm_bf16x3(const void* A, int lda, const void* W, int ldw, const float* bias, const float* residual,
+                                int ldr, void* C, int ldc, int c_split, int M, int N, int K, int epilogue,
+                                cudaStream_t stream) {
+  PFPP_CHECK_ARG(A && W && C && M >= 0 && N > 0 && K > 0);
+  PFPP_CHECK_ARG((K % 8) == 0 && (lda % 16) == 0 && (ldw % 16) == 0 && lda >= 2 * K && ldw >= 2 * K);
+  PFPP_CHECK_ARG((((uintptr_t)A) & 15) == 0 && (((uintptr_t)W) & 15) == 0);
+  PFPP_CHECK_ARG(!c_split || (ldc % 2) == 0);
+  if (M == 0) return PFPP_OK;
+  const __nv_bfloat16* a = (const __nv_bfloat16*)A;
+  const __nv_bfloat16* w = (const __nv_bfloat16*)W;
+  return gemm_dispatch(a, a + lda / 2, lda, w, w + ldw / 2, ldw, bias, residual, ldr, C, ldc, ldc / 2, c_split ? 2 : 0, M, N,
+                       K, epilogue, stream);
 }

@@ -376,6 +376,32 @@ __global__ void group_gather_kernel(const float* __restrict__ xyz, const float* 
   }
 }
 
+// split variant (fp32-grade tensor-core path): features are bf16 hi/lo rows [K, N, 2D] (lo at D + c) and are copied
+// as they are; the centroid offsets are split here.  out rows hold 2*ld elements: hi at c, lo at ld + c.
+__global__ void group_gather_split_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                                          const __nv_bfloat16* __restrict__ feats, const int* __restrict__ gidx, int N,
+                                          int S, int ns, int D, int ld, long long rows, __nv_bfloat16* __restrict__ out) {
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int lane = threadIdx.x & 31;
+  long long ks = row / ns;  // k*S + s
+  int k = (int)(ks / S);
+  int idx = gidx[row];
+  __nv_bfloat16* o = out + row * (2 * ld);
+  if (lane < 3) {
+    float v = fsub(xyz[((size_t)k * N + idx) * 3 + lane], new_xyz[ks * 3 + lane]);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    o[lane] = h;
+    o[ld + lane] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+  const __nv_bfloat16* f = feats ? feats + ((size_t)k * N + idx) * (2 * D) : nullptr;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  for (int c = lane; c < ld - 3; c += 32) {
+    o[3 + c] = (f && c < D) ? f[c] : zero;
+    o[ld + 3 + c] = (f && c < D) ? f[D + c] : zero;
+  }
+}
+
 extern "C" int pfpp_group_gather(const float* xyz, const float* new_xyz, const void* feats, const int* gidx, int K,
                                  int N, int S, int ns, int D, int ld, int out_bf16, void* out,
                                  cudaStream_t stream) {
@@ -383,7 +409,10 @@ extern "C" int pfpp_group_gather(const float* xyz, const float* new_xyz, const v
   long long rows = (long long)K * S * ns;
   if (rows == 0) return PFPP_OK;
   int grid = pfpp_cdiv(rows, 8);
-  if (out_bf16)
+  if (out_bf16 == 2)
+    group_gather_split_kernel<<<grid, 256, 0, stream>>>(xyz, new_xyz, (const __nv_bfloat16*)feats, gidx, N, S, ns, D, ld,
+                                                        rows, (__nv_bfloat16*)out);
+  else if (out_bf16)
     group_gather_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>(
         xyz, new_xyz, (const __nv_bfloat16*)feats, gidx, N, S, ns, D, ld, rows, (__nv_bfloat16*)out);
   else
@@ -405,12 +434,29 @@ __global__ void group_max_kernel(const T* __restrict__ in, int ns, int C, int ld
   }
 }
 
+// fp32 rows in, bf16 hi/lo split rows out (ld_out elements: hi at c, lo at ld_out/2 + c)
+__global__ void group_max_split_kernel(const float* __restrict__ in, int ns, int C, int ld_in, long long G,
+                                       __nv_bfloat16* __restrict__ out, int ld_out) {
+  long long g = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* p = in + (g * ns) * (long long)ld_in + c;
+    float m = p[0];
+    for (int j = 1; j < ns; ++j) m = fmaxf(m, p[(long long)j * ld_in]);
+    const __nv_bfloat16 h = __float2bfloat16_rn(m);
+    out[g * ld_out + c] = h;
+    out[g * ld_out + ld_out / 2 + c] = __float2bfloat16_rn(m - __bfloat162float(h));
+  }
+}
+
 extern "C" int pfpp_group_max(const void* in, long long G, int ns, int C, int ld_in, int is_bf16, void* out,
                               int ld_out, cudaStream_t stream) {
   PFPP_CHECK_ARG(in && out && ns > 0 && C > 0);
   if (G == 0) return PFPP_OK;
   int threads = C >= 256 ? 256 : 128;
-  if (is_bf16)
+  if (is_bf16 == 2)  // fp32 in -> split out
+    group_max_split_kernel<<<(unsigned)G, threads, 0, stream>>>((const float*)in, ns, C, ld_in, G, (__nv_bfloat16*)out,
+                                                               ld_out);
+  else if (is_bf16)
     group_max_kernel<__nv_bfloat16><<<(unsigned)G, threads, 0, stream>>>((const __nv_bfloat16*)in, ns, C, ld_in, G,
                                                                        (__nv_bfloat16*)out, ld_out);
   else

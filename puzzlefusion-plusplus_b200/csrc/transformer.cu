@@ -28,7 +28,44 @@ __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-template <typename OutT>
+// bf16 hi/lo split of an fp32 value (operand format of the fp32-grade bf16x3 contraction, gemm_tc.cu):
+// hi = bf16(v), lo = bf16(v - hi); hi + lo carries 16 mantissa bits of v.
+__device__ __forceinline__ void split_store(__nv_bfloat16* o, int lo_off, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  o[0] = h;
+  o[lo_off] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// x [rows, C] fp32 (leading dimension ldx) -> out [rows, ldo] bf16: hi at column c, lo at ldo/2 + c, zero padding
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long rows, int C, int ldx, __nv_bfloat16* __restrict__ out,
+                                  int ldo) {
+  const int half = ldo >> 1;
+  const long long total = rows * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / half;
+    const int c = (int)(i - r * half);
+    const float v = c < C ? x[r * ldx + c] : 0.f;
+    split_store(out + r * ldo + c, half, v);
+  }
+}
+
+extern "C" int pfpp_split_bf16(const float* x, long long rows, int C, int ldx, void* out, int ldo, cudaStream_t stream) {
+  PFPP_CHECK_ARG(x && out && rows >= 0 && C > 0 && ldx >= C && (ldo % 2) == 0 && ldo / 2 >= C);
+  if (rows == 0) return PFPP_OK;
+  long long total = rows * (ldo / 2);
+  int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  split_bf16_kernel<<<grid, 256, 0, stream>>>(x, rows, C, ldx, (__nv_bfloat16*)out, ldo);
+  PFPP_RETURN_LAST();
+}
+
+// SPLIT: OutT is bf16 and every value is written as a hi/lo pair (lo at column offset ld/2 of the same row)
+template <typename OutT, bool SPLIT>
+__device__ __forceinline__ void put_out(OutT* o, int lo_off, float v) {
+  if constexpr (SPLIT) split_store(o, lo_off, v);
+  else *o = cvt_out<OutT>(v);
+}
+
+template <typename OutT, bool SPLIT>
 __global__ void embed_features_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                       const int* __restrict__ frag_slot, const float* __restrict__ latent,
                                       const float* __restrict__ xyz, int F, int L, int latent_dim,
@@ -41,12 +78,13 @@ __global__ void embed_features_kernel(const float* __restrict__ x, const float* 
     float p[3] = {xyz[(size_t)row * 3], xyz[(size_t)row * 3 + 1], xyz[(size_t)row * 3 + 2]};
     float s = scale[slot];
     OutT* o = feat_tok + (size_t)row * ld_tok;
-    for (int c = threadIdx.x; c < ld_tok; c += blockDim.x) {
+    const int w_tok = SPLIT ? ld_tok / 2 : ld_tok;
+    for (int c = threadIdx.x; c < w_tok; c += blockDim.x) {
       float v = 0.f;
       if (c < latent_dim) v = latent[(size_t)row * latent_dim + c];
       else if (c < latent_dim + 63) v = nerf_feature(p, 3, c - latent_dim);
       else if (c < latent_dim + 84) v = nerf_feature(&s, 1, c - latent_dim - 63);
-      o[c] = cvt_out<OutT>(v);
+      put_out<OutT, SPLIT>(o + c, w_tok, v);
     }
   } else {
     int f = row - F * L;
@@ -55,7 +93,9 @@ __global__ void embed_features_kernel(const float* __restrict__ x, const float* 
 #pragma unroll
     for (int i = 0; i < 7; ++i) v7[i] = x[(size_t)slot * 7 + i];
     OutT* o = feat_par + (size_t)f * ld_par;
-    for (int c = threadIdx.x; c < ld_par; c += blockDim.x) o[c] = cvt_out<OutT>(c < 147 ? nerf_feature(v7, 7, c) : 0.f);
+    const int w_par = SPLIT ? ld_par / 2 : ld_par;
+    for (int c = threadIdx.x; c < w_par; c += blockDim.x)
+      put_out<OutT, SPLIT>(o + c, w_par, c < 147 ? nerf_feature(v7, 7, c) : 0.f);
   }
 }
 
@@ -63,15 +103,20 @@ extern "C" int pfpp_embed_features(const float* x, const float* scale, const int
                                    const float* xyz, int F, int L, int latent_dim, int out_bf16, void* feat_tok,
                                    int ld_tok, void* feat_par, int ld_par, cudaStream_t stream) {
   PFPP_CHECK_ARG(x && scale && frag_slot && latent && xyz && feat_tok && feat_par);
-  PFPP_CHECK_ARG(ld_tok >= latent_dim + 84 && ld_par >= 147);
+  const int div = out_bf16 == 2 ? 2 : 1;  // out_bf16 == 2: bf16 hi/lo split rows of ld_* elements (two halves)
+  PFPP_CHECK_ARG(ld_tok / div >= latent_dim + 84 && ld_par / div >= 147 && out_bf16 >= 0 && out_bf16 <= 2);
   if (F == 0) return PFPP_OK;
-  if (out_bf16)
-    embed_features_kernel<__nv_bfloat16><<<F * L + F, 64, 0, stream>>>(x, scale, frag_slot, latent, xyz, F, L, latent_dim,
-                                                                      (__nv_bfloat16*)feat_tok, ld_tok,
-                                                                      (__nv_bfloat16*)feat_par, ld_par);
+  if (out_bf16 == 2)
+    embed_features_kernel<__nv_bfloat16, true><<<F * L + F, 64, 0, stream>>>(x, scale, frag_slot, latent, xyz, F, L,
+                                                                            latent_dim, (__nv_bfloat16*)feat_tok, ld_tok,
+                                                                            (__nv_bfloat16*)feat_par, ld_par);
+  else if (out_bf16)
+    embed_features_kernel<__nv_bfloat16, false><<<F * L + F, 64, 0, stream>>>(x, scale, frag_slot, latent, xyz, F, L,
+                                                                             latent_dim, (__nv_bfloat16*)feat_tok, ld_tok,
+                                                                             (__nv_bfloat16*)feat_par, ld_par);
   else
-    embed_features_kernel<float><<<F * L + F, 64, 0, stream>>>(x, scale, frag_slot, latent, xyz, F, L, latent_dim,
-                                                              (float*)feat_tok, ld_tok, (float*)feat_par, ld_par);
+    embed_features_kernel<float, false><<<F * L + F, 64, 0, stream>>>(x, scale, frag_slot, latent, xyz, F, L, latent_dim,
+                                                                     (float*)feat_tok, ld_tok, (float*)feat_par, ld_par);
   PFPP_RETURN_LAST();
 }
 
@@ -108,7 +153,7 @@ extern "C" int pfpp_combine_embed(const float* shape_emb, const float* x_emb, co
 //   y = LN(x) * (1 + mod[g, 0:C]) + mod[g, C:2C]     (AdaLN, g = row_group[row / rows_per_group])
 // Optionally post-LN residual form y = LN(x + r).
 // ---------------------------------------------------------------------------------------------
-template <int C, typename OutT>
+template <int C, typename OutT, bool SPLIT>
 __global__ void __launch_bounds__(256)
     layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ mod, const int* __restrict__ row_group,
@@ -156,6 +201,15 @@ __global__ void __launch_bounds__(256)
       const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
       o[0] = o[0] * ga.x + be.x, o[1] = o[1] * ga.y + be.y, o[2] = o[2] * ga.z + be.z, o[3] = o[3] * ga.w + be.w;
     }
+    if constexpr (SPLIT) {  // bf16 hi/lo rows of 2C elements: hi at c, lo at C + c
+      __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(y) + row * (2 * C) + c;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      __nv_bfloat162 l0 = __floats2bfloat162_rn(o[0] - f0.x, o[1] - f0.y), l1 = __floats2bfloat162_rn(o[2] - f1.x, o[3] - f1.y);
+      *reinterpret_cast<uint2*>(ys) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(ys + C) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+      continue;
+    }
     OutT* yo = y + row * C + c;
     if (sizeof(OutT) == 2) {  // bf16: one 8-byte store per lane
       __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
@@ -173,15 +227,17 @@ extern "C" int pfpp_layernorm(const float* x, const float* residual, const float
   PFPP_CHECK_ARG(!mod || (row_group && rows_per_group > 0));
   if (rows == 0) return PFPP_OK;
   int grid = pfpp_cdiv(rows, 8);
-#define PFPP_LN_CASE(CC, T)                                                                                   \
-  layernorm_kernel<CC, T><<<grid, 256, 0, stream>>>(x, residual, gamma, beta, mod, row_group, rows_per_group, \
-                                                    rows, (T*)y, sum_out)
+#define PFPP_LN_CASE(CC, T, SP)                                                                                   \
+  layernorm_kernel<CC, T, SP><<<grid, 256, 0, stream>>>(x, residual, gamma, beta, mod, row_group, rows_per_group, \
+                                                        rows, (T*)y, sum_out)
   if (C == 512) {
-    if (out_bf16) PFPP_LN_CASE(512, __nv_bfloat16);
-    else PFPP_LN_CASE(512, float);
+    if (out_bf16 == 2) PFPP_LN_CASE(512, __nv_bfloat16, true);
+    else if (out_bf16) PFPP_LN_CASE(512, __nv_bfloat16, false);
+    else PFPP_LN_CASE(512, float, false);
   } else {
-    if (out_bf16) PFPP_LN_CASE(256, __nv_bfloat16);
-    else PFPP_LN_CASE(256, float);
+    if (out_bf16 == 2) PFPP_LN_CASE(256, __nv_bfloat16, true);
+    else if (out_bf16) PFPP_LN_CASE(256, __nv_bfloat16, false);
+    else PFPP_LN_CASE(256, float, false);
   }
 #undef PFPP_LN_CASE
   PFPP_RETURN_LAST();
@@ -200,7 +256,7 @@ extern "C" int pfpp_layernorm(const float* x, const float* residual, const float
 // ---------------------------------------------------------------------------------------------
 #define ATT_KT 32
 
-template <int D, typename InT, typename OutT>
+template <int D, typename InT, typename OutT, bool SPLIT>
 __global__ void __launch_bounds__(128)
     attn_varlen_kernel(const InT* __restrict__ qkv, int ld, int q_off, int k_off, int v_off,
                        const int* __restrict__ seg_start, const int* __restrict__ seg_len, float scale,
@@ -270,7 +326,7 @@ __global__ void __launch_bounds__(128)
     float inv = 1.0f / l;
     OutT* o = out + (size_t)(st + qi) * ldo + h * D;
 #pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = cvt_out<OutT>(acc[d] * inv);
+    for (int d = 0; d < D; ++d) put_out<OutT, SPLIT>(o + d, ldo / 2, acc[d] * inv);
   }
 }
 
@@ -282,15 +338,18 @@ extern "C" int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_o
   int threads = max_len >= 128 ? 128 : ((max_len + 31) / 32) * 32;
   dim3 grid(pfpp_cdiv(max_len, threads), heads, n_segments);
   float scale = 1.0f / sqrtf((float)head_dim);
-#define PFPP_ATT_CASE(DD, TI, TO)                                                                            \
-  attn_varlen_kernel<DD, TI, TO><<<grid, threads, 0, stream>>>((const TI*)qkv, ld, q_off, k_off, v_off, \
-                                                               seg_start, seg_len, scale, (TO*)out, ldo)
+#define PFPP_ATT_CASE(DD, TI, TO, SP)                                                                        \
+  attn_varlen_kernel<DD, TI, TO, SP><<<grid, threads, 0, stream>>>((const TI*)qkv, ld, q_off, k_off, v_off, \
+                                                                   seg_start, seg_len, scale, (TO*)out, ldo)
+  // io_bf16: 0 = fp32 in / fp32 out, 1 = bf16 / bf16, 2 = fp32 in / bf16 hi-lo split out (rows of ldo = 2C elements)
   if (head_dim == 64) {
-    if (io_bf16) PFPP_ATT_CASE(64, __nv_bfloat16, __nv_bfloat16);
-    else PFPP_ATT_CASE(64, float, float);
+    if (io_bf16 == 2) PFPP_ATT_CASE(64, float, __nv_bfloat16, true);
+    else if (io_bf16) PFPP_ATT_CASE(64, __nv_bfloat16, __nv_bfloat16, false);
+    else PFPP_ATT_CASE(64, float, float, false);
   } else {
-    if (io_bf16) PFPP_ATT_CASE(32, __nv_bfloat16, __nv_bfloat16);
-    else PFPP_ATT_CASE(32, float, float);
+    if (io_bf16 == 2) PFPP_ATT_CASE(32, float, __nv_bfloat16, true);
+    else if (io_bf16) PFPP_ATT_CASE(32, __nv_bfloat16, __nv_bfloat16, false);
+    else PFPP_ATT_CASE(32, float, float, false);
   }
 #undef PFPP_ATT_CASE
   PFPP_RETURN_LAST();

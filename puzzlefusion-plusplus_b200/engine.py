@@ -12,8 +12,14 @@
 
 Everything here is launch plumbing: torch is used for device memory and streams only; every op on the
 path is a kernel of libpfpp_sm100.so called through the C ABI.  ``precision`` selects the contraction
-engine: "fp32" = SIMT FFMA GEMMs with fp32 activations (parity mode), "bf16" = tcgen05/TMEM GEMMs with
-bf16 activations and fp32 accumulation / residual stream (fast mode).
+engine:
+  "fp32" = SIMT FFMA GEMMs with fp32 activations (the plain parity mode);
+  "bf16" = tcgen05/TMEM GEMMs, fused set abstraction and attention with bf16 operands, fp32 accumulation and an
+           fp32 residual stream (fast mode);
+  "tc32" = tensor-core parity mode: every contraction runs on tcgen05 with bf16 hi/lo SPLIT operands
+           (a = a_hi + a_lo, three MMA passes a_hi w_hi + a_lo w_hi + a_hi w_lo into one fp32 accumulator, relative
+           error 2^-16 per product instead of bf16's 2^-8), activations travel between kernels as hi/lo pairs, softmax
+           attention stays fp32 SIMT.  The verifier uses the same split GEMMs in "bf16" and "tc32" modes.
 """
 import gc
 
@@ -42,15 +48,18 @@ class Engine:
                  freeze_gc=False):
         if not torch.cuda.is_available():
             raise _lib.PfppError("pfpp-b200 needs a CUDA device (sm_100a); there is no CPU path")
-        if precision not in ("bf16", "fp32"):
+        if precision not in ("bf16", "fp32", "tc32"):
             raise ValueError(precision)
         _lib.load()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.bf16 = precision == "bf16"
+        self.tc32 = precision == "tc32"
         self.precision = precision
-        self.act_dtype = torch.bfloat16 if self.bf16 else torch.float32
-        self.kmult = 8 if self.bf16 else 4
+        self.mode = {"fp32": 0, "bf16": 1, "tc32": 2}[precision]  # the out_bf16 / io_bf16 flag of the kernels
+        self.act_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.wm = 2 if self.tc32 else 1  # activation rows hold hi | lo halves in tc32 mode
+        self.kmult = 4 if precision == "fp32" else 8
         self.P, self.L, self.latent_dim, self.heads = max_parts, latent_points, latent_dim, heads
         self.sa_cfg = tuple(sa_cfg)
         self.chunk = chunk_frags
@@ -58,9 +67,12 @@ class Engine:
         self.sched.set_timesteps(num_inference_steps)
         self.T = num_inference_steps
         self.coef = self.sched.coefficient_table().contiguous().to(self.device)  # [T,5]
-        self.enc = EncoderWeights(ckpt["encoder"], self.device, self.bf16)
-        self.den = DenoiserWeights(ckpt["denoiser"], self.device, self.bf16, num_layers, self.sched.timesteps)
-        self.ver = VerifierWeights(ckpt["verifier"], self.device, verifier_layers) if "verifier" in ckpt else None
+        self.enc = EncoderWeights(ckpt["encoder"], self.device, self.bf16, self.tc32)
+        self.den = DenoiserWeights(ckpt["denoiser"], self.device, self.bf16, num_layers, self.sched.timesteps, self.tc32)
+        # the verifier's projections / FFN run as split (fp32-grade) tensor-core GEMMs unless the engine is plain fp32
+        self.verifier_tc = precision != "fp32"
+        self.ver = (VerifierWeights(ckpt["verifier"], self.device, verifier_layers, self.verifier_tc)
+                    if "verifier" in ckpt else None)
         self.C = self.den.C
         self.tc_attention = True  # tcgen05 attention in bf16 mode (segments > 512 tokens stream K/V through a ring)
         self.fused_sa = True     # fused gather + 3-layer MLP + max tcgen05 kernel in bf16 mode
@@ -148,11 +160,18 @@ class Engine:
         torch.cuda.current_stream().synchronize()
         return {k: v.clone() for k, v in views.items()}
 
-    def gemm(self, a, lda, lin, out, ldc, M, epi=EPI_NONE, residual=None, ldr=0, out_bf16=None, force_f32=False):
+    def gemm(self, a, lda, lin, out, ldc, M, epi=EPI_NONE, residual=None, ldr=0, out_bf16=None, force_f32=False,
+             split=None):
         """out[M, N'] = epi(a[M,K] @ W^T + b) (+ residual) on the engine selected by the precision mode."""
+        split = self.tc32 if split is None else split
         bias = _lib.ptr(lin.b)
         res = _lib.ptr(residual)
-        if self.bf16 and not force_f32:
+        if split and not force_f32:
+            # bf16 hi/lo split operands (rows of 2*lda / 2*ldw elements), fp32 or split output
+            so = (out.dtype == torch.bfloat16) if out_bf16 is None else out_bf16
+            call("pfpp_gemm_bf16x3", a.data_ptr(), 2 * lda, lin.w16s.data_ptr(), 2 * lin.k16, bias, res, ldr, out.data_ptr(),
+                 2 * ldc if so else ldc, int(so), M, lin.n, lin.k16, epi)
+        elif self.bf16 and not force_f32:
             ob = (out.dtype == torch.bfloat16) if out_bf16 is None else out_bf16
             call("pfpp_gemm_bf16", a.data_ptr(), lda, lin.w16.data_ptr(), lin.k16, bias, res, ldr, out.data_ptr(), ldc,
                  int(ob), M, lin.n, lin.k16, epi)
@@ -179,25 +198,31 @@ class Engine:
     def encode(self, part_pcs, frag_slot, x, N, trace=None):
         """part_pcs [slots,N,3], frag_slot int32 [F], x [slots,7] -> latent [F*L,64] fp32, xyz [F,L,3] fp32."""
         F = frag_slot.numel()
-        L, act, bf = self.L, self.act_dtype, int(self.bf16)
+        L, act, bf, wm = self.L, self.act_dtype, self.mode, self.wm
         z_e = self.buf("z_e", (F * L, self.latent_dim), torch.float32)
         xyz_out = self.buf("xyz3", (F, L, 3), torch.float32)
         latent = self.buf("latent", (F * L, self.latent_dim), torch.float32)
         # the fused path keeps activations on chip, so nothing needs chunking; the unfused path bounds its
         # [rows, C] intermediates by processing `chunk` fragments at a time
-        Fc = F if (self.bf16 and self.fused_sa) else min(self.chunk, F)
+        chans = [[lin.n for lin in layers] for layers in self.enc.sa]
+        # the fused kernel keeps these intermediates on chip (only when every level has a fused instantiation)
+        fused = self.bf16 and self.fused_sa and all(
+            (ns, d, c[0], c[1], c[2]) in self._FUSED_LEVELS
+            for (_, _, ns), d, c in zip(self.sa_cfg, (0, chans[0][2], chans[1][2]), chans))
+        Fc = F if fused else min(self.chunk, F)
         rot = self.buf("rot", (Fc, N, 3), torch.float32)
         max_rows = Fc * max(s * ns for s, _, ns in self.sa_cfg)
         gidx = self.buf("gidx", (max_rows,), torch.int32)
-        chans = [[lin.n for lin in layers] for layers in self.enc.sa]
         kin = [self._pad(3 + d) for d in (0, chans[0][2], chans[1][2])]
-        X = self.buf("saX", (max(Fc * s * ns * k for (s, _, ns), k in zip(self.sa_cfg, kin)),), act)
-        B1 = self.buf("saB1", (max(Fc * s * ns * c[0] for (s, _, ns), c in zip(self.sa_cfg, chans)),), act)
-        B2 = self.buf("saB2", (max(Fc * s * ns * c[1] for (s, _, ns), c in zip(self.sa_cfg, chans)),), act)
-        B3 = self.buf("saB3", (max(Fc * s * ns * c[2] for (s, _, ns), c in zip(self.sa_cfg, chans)),), act)
+        X = self.buf("saX", (1 if fused else wm * max(Fc * s * ns * k for (s, _, ns), k in zip(self.sa_cfg, kin)),), act)
+        B1 = self.buf("saB1", (1 if fused else wm * max(Fc * s * ns * c[0] for (s, _, ns), c in zip(self.sa_cfg, chans)),), act)
+        B2 = self.buf("saB2", (1 if fused else wm * max(Fc * s * ns * c[1] for (s, _, ns), c in zip(self.sa_cfg, chans)),), act)
+        # the last MLP layer feeds the max over nsample: fp32 in tc32 mode (the max kernel re-splits its result)
+        B3 = self.buf("saB3", (1 if fused else max(Fc * s * ns * c[2] for (s, _, ns), c in zip(self.sa_cfg, chans)),),
+                      torch.float32 if self.tc32 else act)
         idx = [self.buf(f"fpsidx{i}", (Fc, s), torch.int32) for i, (s, _, _) in enumerate(self.sa_cfg)]
         cxyz = [self.buf(f"fpsxyz{i}", (Fc, s, 3), torch.float32) for i, (s, _, _) in enumerate(self.sa_cfg)]
-        feats = [self.buf(f"safeat{i}", (Fc, s, c[2]), act) for i, ((s, _, _), c) in enumerate(zip(self.sa_cfg, chans))]
+        feats = [self.buf(f"safeat{i}", (Fc, s, wm * c[2]), act) for i, ((s, _, _), c) in enumerate(zip(self.sa_cfg, chans))]
         for c0 in range(0, F, Fc):
             K = min(Fc, F - c0)
             slot_ptr = frag_slot.data_ptr() + 4 * c0
@@ -215,7 +240,7 @@ class Engine:
                 rows = K * S * ns
                 ld = kin[li]
                 l0, l1, l2 = self.enc.sa[li]
-                if self.bf16 and self.fused_sa and (ns, src_d, l0.n, l1.n, l2.n) in self._FUSED_LEVELS:
+                if fused:
                     call("pfpp_sa_fused", self._FUSED_LEVELS[(ns, src_d, l0.n, l1.n, l2.n)], src_xyz.data_ptr(),
                          cx.data_ptr(), _lib.ptr(src_feat), gidx.data_ptr(), K, src_n, S, _lib.ptr(l0.w16_feat),
                          l0.wxyz.data_ptr(), l0.b.data_ptr(), l1.w16.data_ptr(), l1.b.data_ptr(), l2.w16.data_ptr(),
@@ -233,17 +258,18 @@ class Engine:
                 self.gemm(X, ld, l0, B1, l0.n, rows, EPI_RELU)
                 self.gemm(B1, l0.n, l1, B2, l1.n, rows, EPI_RELU)
                 self.gemm(B2, l1.n, l2, B3, l2.n, rows, EPI_RELU)
-                call("pfpp_group_max", B3.data_ptr(), K * S, ns, l2.n, l2.n, bf, feats[li].data_ptr(), l2.n)
+                call("pfpp_group_max", B3.data_ptr(), K * S, ns, l2.n, l2.n, bf, feats[li].data_ptr(), wm * l2.n)
                 if trace is not None:
                     trace.setdefault(f"sa{li + 1}.fps_idx", []).append(idx[li][:K].clone())
                     trace.setdefault(f"sa{li + 1}.group_idx", []).append(gidx[:rows].view(K, S, ns).clone())
-                    trace.setdefault(f"sa{li + 1}.feats", []).append(feats[li][:K].float().clone())
+                    ft = feats[li][:K].float()
+                    trace.setdefault(f"sa{li + 1}.feats", []).append((ft[..., :l2.n] + ft[..., l2.n:]) if self.tc32 else ft.clone())
                     if li == 0:
                         trace.setdefault("rotated", []).append(rot[:K].clone())
                 src_xyz, src_n, src_feat, src_d = cx, S, feats[li], l2.n
             # conv6 (pn2.py:65): fp32 output for the code search
             c6 = self.enc.conv6
-            self.gemm(feats[2], c6.k16 if self.bf16 else c6.k32, c6, z_e[c0 * L:], self.latent_dim, K * L, EPI_NONE,
+            self.gemm(feats[2], c6.k32 if self.mode == 0 else c6.k16, c6, z_e[c0 * L:], self.latent_dim, K * L, EPI_NONE,
                       out_bf16=False)
         codes = self.buf("codes", (F * L * 4,), torch.int32)
         call("pfpp_vq", z_e.data_ptr(), 0, F * L * (self.latent_dim // 16), self.enc.codebook.data_ptr(),
@@ -258,23 +284,24 @@ class Engine:
                     trace=None):
         """One DenoiserTransformer forward on the packed batch -> eps [F, 8] fp32 (cols 0..6 used)."""
         F = frag_slot.numel()
-        L, C, H, act, bf = self.L, self.C, self.heads, self.act_dtype, int(self.bf16)
+        L, C, H, act, bf, wm = self.L, self.C, self.heads, self.act_dtype, self.mode, self.wm
         M = F * L
         D = C // H
         w = self.den
         ld_tok = self._pad(self.latent_dim + 84)
         ld_par = self._pad(147)
-        feat_tok = self.buf("feat_tok", (M, ld_tok), act)
-        feat_par = self.buf("feat_par", (F, ld_par), act)
+        feat_tok = self.buf("feat_tok", (M, wm * ld_tok), act)
+        feat_par = self.buf("feat_par", (F, wm * ld_par), act)
         shape_emb = self.buf("shape_emb", (M, C), torch.float32)
         x_emb = self.buf("x_emb", (F, C), torch.float32)
         h = self.buf("h", (M, C), torch.float32)
-        ln = self.buf("ln", (M, C), act)
-        qkv = self.buf("qkv", (M, 3 * C), act)
-        ao = self.buf("ao", (M, C), act)
-        ff = self.buf("ff", (M, 4 * C), act)
+        ln = self.buf("ln", (M, wm * C), act)
+        # tc32: q/k/v stay fp32 for the fp32 softmax attention, whose output is split again for the out-projection
+        qkv = self.buf("qkv", (M, 3 * C), torch.float32 if self.tc32 else act)
+        ao = self.buf("ao", (M, wm * C), act)
+        ff = self.buf("ff", (M, wm * 4 * C), act)
         call("pfpp_embed_features", x.data_ptr(), scale.data_ptr(), frag_slot.data_ptr(), latent.data_ptr(),
-             xyz.data_ptr(), F, L, self.latent_dim, bf, feat_tok.data_ptr(), ld_tok, feat_par.data_ptr(), ld_par)
+             xyz.data_ptr(), F, L, self.latent_dim, bf, feat_tok.data_ptr(), wm * ld_tok, feat_par.data_ptr(), wm * ld_par)
         self.gemm(feat_tok, ld_tok, w.shape_embedding, shape_emb, C, M)
         self.gemm(feat_par, ld_par, w.param_fc, x_emb, C, F)
         call("pfpp_combine_embed", shape_emb.data_ptr(), x_emb.data_ptr(), w.ref_emb.data_ptr(), w.pe.data_ptr(),
@@ -301,7 +328,7 @@ class Engine:
                          5 * L * self.local_tiles, H, L, ao.data_ptr(), C)
                 else:
                     call("pfpp_attention_varlen", qkv.data_ptr(), 3 * C, 0, C, 2 * C, segs[0].data_ptr(),
-                         segs[1].data_ptr(), nseg, mlen, H, D, bf, ao.data_ptr(), C)
+                         segs[1].data_ptr(), nseg, mlen, H, D, bf, ao.data_ptr(), wm * C)
                 self.gemm(ao, C, lw[name + ".out"], h, C, M, EPI_NONE, residual=h, ldr=C)
             call("pfpp_layernorm", h.data_ptr(), None, lw["norm3.w"].data_ptr(), lw["norm3.b"].data_ptr(), None, None, 0, M,
                  C, bf, ln.data_ptr(), None)
@@ -326,30 +353,46 @@ class Engine:
     def verifier_logits(self, feat, tok_row, tok_i, tok_j, seg_start, seg_len, max_len, n_rows):
         """feat [n_rows,7] fp32 dense edge features; packed valid-edge tokens -> logits [n_rows] fp32.
 
-        Always fp32 (the 0.9 acceptance threshold is applied to these logits)."""
+        fp32-grade in every mode (the 0.9 acceptance threshold is applied to these logits): SIMT fp32
+        GEMMs in "fp32" mode, split-operand tcgen05 GEMMs (pfpp_gemm_bf16x3, fp32 accumulate / residual / LayerNorm /
+        softmax) otherwise."""
         w = self.ver
         C, H = w.C, self.heads
         n = tok_row.numel()
+        tc = self.verifier_tc
+        ffn = w.layers[0]["l1"].n
         h = self.buf("v_h", (n, C), torch.float32)
         h2 = self.buf("v_h2", (n, C), torch.float32)
         qkv = self.buf("v_qkv", (n, 3 * C), torch.float32)
-        ao = self.buf("v_ao", (n, C), torch.float32)
         t1 = self.buf("v_t1", (n, C), torch.float32)
-        ffb = self.buf("v_ff", (n, w.layers[0]["l1"].n), torch.float32)
         logits = self.buf("v_logits", (n_rows,), torch.float32)
         logits.zero_()
+        if tc:
+            # split (hi | lo) bf16 operands for the tensor-core GEMMs; residual stream, LayerNorm and softmax stay fp32
+            hs = self.buf("v_hs", (n, 2 * C), torch.bfloat16)
+            ao = self.buf("v_ao", (n, 2 * C), torch.bfloat16)
+            ffb = self.buf("v_ff", (n, 2 * ffn), torch.bfloat16)
+        else:
+            ao = self.buf("v_ao", (n, C), torch.float32)
+            ffb = self.buf("v_ff", (n, ffn), torch.float32)
         call("pfpp_verifier_embed", feat.data_ptr(), tok_row.data_ptr(), tok_i.data_ptr(), tok_j.data_ptr(), n,
              w.emb_w.data_ptr(), w.emb_b.data_ptr(), w.pe.data_ptr(), C, h.data_ptr())
+
+        def operand(t):  # fp32 [n, C] -> the A operand of the next projection
+            if not tc:
+                return t
+            call("pfpp_split_bf16", t.data_ptr(), n, C, C, hs.data_ptr(), 2 * C)
+            return hs
         for lw in w.layers:
-            self.gemm(h, C, lw["qkv"], qkv, 3 * C, n, force_f32=True)
+            self.gemm(operand(h), C, lw["qkv"], qkv, 3 * C, n, force_f32=not tc, split=tc)
             call("pfpp_attention_varlen", qkv.data_ptr(), 3 * C, 0, C, 2 * C, seg_start.data_ptr(), seg_len.data_ptr(),
-                 seg_start.numel(), max_len, H, C // H, 0, ao.data_ptr(), C)
-            self.gemm(ao, C, lw["out"], t1, C, n, force_f32=True)
+                 seg_start.numel(), max_len, H, C // H, 2 if tc else 0, ao.data_ptr(), 2 * C if tc else C)
+            self.gemm(ao, C, lw["out"], t1, C, n, force_f32=not tc, split=tc)
             # x = LN1(x + attn)      (post-LN TransformerEncoderLayer, SURVEY App. B.5)
             call("pfpp_layernorm", h.data_ptr(), t1.data_ptr(), lw["n1w"].data_ptr(), lw["n1b"].data_ptr(), None, None, 0,
                  n, C, 0, h2.data_ptr(), None)
-            self.gemm(h2, C, lw["l1"], ffb, lw["l1"].n, n, EPI_GELU, force_f32=True)
-            self.gemm(ffb, lw["l1"].n, lw["l2"], t1, C, n, force_f32=True)
+            self.gemm(operand(h2), C, lw["l1"], ffb, ffn, n, EPI_GELU, force_f32=not tc, split=tc)
+            self.gemm(ffb, ffn, lw["l2"], t1, C, n, force_f32=not tc, split=tc)
             # x = LN2(x + ff)
             call("pfpp_layernorm", h2.data_ptr(), t1.data_ptr(), lw["n2w"].data_ptr(), lw["n2b"].data_ptr(), None, None, 0,
                  n, C, 0, h.data_ptr(), None)

@@ -30,16 +30,23 @@ def _pad_k(w, mult):
 class Linear:
     """One packed projection: fp32 [N, K4] (+ optional bf16 [N, K8]) and fp32 bias."""
 
-    def __init__(self, w, b, device, bf16):
+    def __init__(self, w, b, device, bf16, split=False):
         w = w.detach().to(torch.float32)
         self.n, self.k = w.shape
         self.w32 = _pad_k(w, 4).to(device)
         self.k32 = self.w32.shape[1]
         self.b = None if b is None else b.detach().to(torch.float32).contiguous().to(device)
-        self.w16 = None
-        if bf16:
-            self.w16 = _pad_k(w, 8).to(device).to(torch.bfloat16).contiguous()
-            self.k16 = self.w16.shape[1]
+        self.w16 = self.w16s = None
+        if bf16 or split:
+            wp = _pad_k(w, 8).to(device)
+            self.k16 = wp.shape[1]
+            if bf16:
+                self.w16 = wp.to(torch.bfloat16).contiguous()
+            if split:
+                # bf16 hi/lo split rows [N, 2*K8] (hi | lo): the weight operand of pfpp_gemm_bf16x3
+                hi = wp.to(torch.bfloat16)
+                lo = (wp - hi.float()).to(torch.bfloat16)
+                self.w16s = torch.cat([hi, lo], 1).contiguous()
 
 
 def fold_bn(sd, prefix, i):
@@ -54,13 +61,13 @@ def fold_bn(sd, prefix, i):
 
 
 class EncoderWeights:
-    def __init__(self, sd, device, bf16):
+    def __init__(self, sd, device, bf16, split=False):
         self.sa = []
         for li in range(3):
             layers = []
             for i in range(3):
                 w, b = fold_bn(sd, f"pn2.sa{li + 1}", i)
-                layers.append(Linear(w, b, device, bf16))
+                layers.append(Linear(w, b, device, bf16, split))
             self.sa.append(layers)
             if bf16:
                 # layer 0 of the fused kernel: feature columns on the tensor cores (bf16), the three
@@ -71,12 +78,12 @@ class EncoderWeights:
                 wx = torch.zeros(w0.n, 4)
                 wx[:, :3] = w[:, :3]
                 w0.wxyz = wx.contiguous().to(device)
-        self.conv6 = Linear(sd["pn2.conv6.weight"].flatten(1), sd["pn2.conv6.bias"], device, bf16)
+        self.conv6 = Linear(sd["pn2.conv6.weight"].flatten(1), sd["pn2.conv6.bias"], device, bf16, split)
         self.codebook = sd["vector_quantization.embedding.weight"].detach().float().contiguous().to(device)
 
 
 class DenoiserWeights:
-    def __init__(self, sd, device, bf16, num_layers, timesteps):
+    def __init__(self, sd, device, bf16, num_layers, timesteps, split=False):
         C = sd["param_fc.weight"].shape[0]
         self.C = C
         self.layers = []
@@ -87,14 +94,14 @@ class DenoiserWeights:
             L = {}
             for a in ("self_attn", "global_attn"):
                 wqkv = torch.cat([sd[f"{p}.{a}.to_q.weight"], sd[f"{p}.{a}.to_k.weight"], sd[f"{p}.{a}.to_v.weight"]], 0)
-                L[a + ".qkv"] = Linear(wqkv, None, device, bf16)
-                L[a + ".out"] = Linear(sd[f"{p}.{a}.to_out.0.weight"], sd[f"{p}.{a}.to_out.0.bias"], device, bf16)
+                L[a + ".qkv"] = Linear(wqkv, None, device, bf16, split)
+                L[a + ".out"] = Linear(sd[f"{p}.{a}.to_out.0.weight"], sd[f"{p}.{a}.to_out.0.bias"], device, bf16, split)
             w1, b1 = sd[f"{p}.ff.net.0.proj.weight"], sd[f"{p}.ff.net.0.proj.bias"]
             half = w1.shape[0] // 2
             wi = torch.stack([w1[:half], w1[half:]], 1).reshape(2 * half, -1)
             bi = torch.stack([b1[:half], b1[half:]], 1).reshape(2 * half)
-            L["ff1"] = Linear(wi, bi, device, bf16)
-            L["ff2"] = Linear(sd[f"{p}.ff.net.2.weight"], sd[f"{p}.ff.net.2.bias"], device, bf16)
+            L["ff1"] = Linear(wi, bi, device, bf16, split)
+            L["ff2"] = Linear(sd[f"{p}.ff.net.2.weight"], sd[f"{p}.ff.net.2.bias"], device, bf16, split)
             L["norm3.w"] = sd[f"{p}.norm3.weight"].detach().float().contiguous().to(device)
             L["norm3.b"] = sd[f"{p}.norm3.bias"].detach().float().contiguous().to(device)
             self.layers.append(L)
@@ -108,8 +115,8 @@ class DenoiserWeights:
                 mods.append(out)
         # mod[(layer*2 + which)] : [T, 2C] -- rows selected per fragment by the current step index
         self.mod = torch.stack(mods, 0).contiguous()
-        self.shape_embedding = Linear(sd["shape_embedding.weight"], sd["shape_embedding.bias"], device, bf16)
-        self.param_fc = Linear(sd["param_fc.weight"], sd["param_fc.bias"], device, bf16)
+        self.shape_embedding = Linear(sd["shape_embedding.weight"], sd["shape_embedding.bias"], device, bf16, split)
+        self.param_fc = Linear(sd["param_fc.weight"], sd["param_fc.bias"], device, bf16, split)
         self.ref_emb = sd["ref_part_emb.weight"].detach().float().contiguous().to(device)
         self.pe = sd["pos_encoding.pe"][0].detach().float().contiguous().to(device)  # [P, C]
         self.head0 = Linear(torch.cat([sd["mlp_out_trans.0.weight"], sd["mlp_out_rot.0.weight"]], 0),
@@ -121,7 +128,7 @@ class DenoiserWeights:
 
 
 class VerifierWeights:
-    def __init__(self, sd, device, num_layers):
+    def __init__(self, sd, device, num_layers, split=False):
         self.C = sd["edge_feature_emb.weight"].shape[0]
         f = lambda k: sd[k].detach().float().contiguous().to(device)  # noqa: E731
         self.emb_w, self.emb_b = f("edge_feature_emb.weight"), f("edge_feature_emb.bias")
@@ -131,10 +138,10 @@ class VerifierWeights:
         for i in range(num_layers):
             p = f"transformer_encoder.layers.{i}"
             self.layers.append({
-                "qkv": Linear(sd[f"{p}.self_attn.in_proj_weight"], sd[f"{p}.self_attn.in_proj_bias"], device, False),
-                "out": Linear(sd[f"{p}.self_attn.out_proj.weight"], sd[f"{p}.self_attn.out_proj.bias"], device, False),
-                "l1": Linear(sd[f"{p}.linear1.weight"], sd[f"{p}.linear1.bias"], device, False),
-                "l2": Linear(sd[f"{p}.linear2.weight"], sd[f"{p}.linear2.bias"], device, False),
+                "qkv": Linear(sd[f"{p}.self_attn.in_proj_weight"], sd[f"{p}.self_attn.in_proj_bias"], device, False, split),
+                "out": Linear(sd[f"{p}.self_attn.out_proj.weight"], sd[f"{p}.self_attn.out_proj.bias"], device, False, split),
+                "l1": Linear(sd[f"{p}.linear1.weight"], sd[f"{p}.linear1.bias"], device, False, split),
+                "l2": Linear(sd[f"{p}.linear2.weight"], sd[f"{p}.linear2.bias"], device, False, split),
                 "n1w": f(f"{p}.norm1.weight"), "n1b": f(f"{p}.norm1.bias"),
                 "n2w": f(f"{p}.norm2.weight"), "n2b": f(f"{p}.norm2.bias"),
             })

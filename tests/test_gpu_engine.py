@@ -61,6 +61,32 @@ def test_encoder_fp32_vs_reference_golden(engines, ckpt):
     assert diff[same].max() <= 2e-4
 
 
+def test_encoder_tc32_vs_reference_golden(engines, ckpt):
+    """tensor-core parity mode (bf16 hi/lo split operands, unfused set abstraction): the fp32-mode tolerances hold --
+    per-level features 2e-4 of scale, z_e 5e-4, >= 97 % equal VQ codes, z_q 2e-4 where the code agrees."""
+    g, latent, xyz, tr = _encode_golden(engines("tc32", 20))
+    assert torch.equal(tr["sa1.fps_idx"][0].cpu().long(), g["sa1_fps_idx"])
+    assert torch.equal(xyz, g["xyz"])
+    otr = {}
+    oe.vqvae_encode(ckpt["encoder"], g["rotated"], trace=otr)
+    for lvl in ("sa1", "sa2", "sa3"):
+        a, b = tr[f"{lvl}.feats"][0].cpu(), otr[f"{lvl}.feats"]
+        assert (a - b).abs().max() <= 2e-4 * max(1.0, b.abs().max()), (lvl, (a - b).abs().max())
+    z_e = tr["z_e"].cpu().reshape(3, 25, 64)
+    assert (z_e - otr["z_e"]).abs().max() <= 5e-4
+    same = tr["codes"].cpu().long().reshape(3, 100) == otr["codes"]
+    assert same.float().mean() >= 0.97, same.float().mean()
+    diff = (latent - g["z_q"]).reshape(3, 100, 16).abs().amax(-1)
+    assert diff[same].max() <= 2e-4
+
+
+def test_denoiser_tc32_vs_reference_golden(engines):
+    """tensor-core parity mode vs the reference's DenoiserTransformer.forward: |eps - eps_ref| <= 1e-4, the
+    tolerance of the SIMT fp32 mode."""
+    g, eps, ref, tr = _denoise_golden(engines("tc32", 100))
+    assert (eps - ref).abs().max() <= 1e-4, (eps - ref).abs().max()
+
+
 def test_encoder_bf16_close(engines, ckpt):
     """fast mode: geometry indices still bit-exact (fp32), features within bf16 tolerance (5e-2 of scale)."""
     g, latent, xyz, tr = _encode_golden(engines("bf16", 20))
@@ -110,8 +136,13 @@ def test_denoiser_bf16_close(engines):
 
 
 def test_verifier_vs_reference_golden(engines):
-    """fp32 verifier logits vs the reference VerifierTransformer on valid edges: <= 2e-4."""
-    e = engines("fp32", 20)
+    """verifier logits vs the reference VerifierTransformer on valid edges: <= 2e-4, with the SIMT fp32 GEMMs (fp32
+    engine) and with the split-operand tcgen05 GEMMs every other engine mode uses."""
+    for mode in ("fp32", "bf16"):
+        _verifier_golden(engines(mode, 20))
+
+
+def _verifier_golden(e):
     g = load_golden("verifier")
     B, E = 2, 190
     feat = g["edge_features"].reshape(B * E, 7).to(DEV).contiguous()

@@ -194,6 +194,69 @@ def test_gemm_bf16_tcgen05(lib, M, N, K, epi, out_bf16):
     assert err <= tol, (err, tol)
 
 
+def _split(t, ld):
+    """fp32 [R, K] -> bf16 hi/lo split rows [R, ld] (hi at c, lo at ld/2 + c), the format of pfpp_gemm_bf16x3"""
+    R, K = t.shape
+    out = torch.zeros(R, ld, dtype=torch.bfloat16)
+    hi = t.to(torch.bfloat16)
+    out[:, :K] = hi
+    out[:, ld // 2:ld // 2 + K] = (t - hi.float()).to(torch.bfloat16)
+    return out
+
+
+@pytest.mark.parametrize("M,N,K,epi,c_split", [(300, 200, 136, 0, 0), (1000, 128, 64, 1, 1), (257, 512, 512, 2, 0),
+                                               (8192, 64, 8, 1, 1), (500, 4096, 512, 4, 1), (640, 1536, 512, 0, 0),
+                                               (100, 64, 512, 0, 0), (16000, 1536, 512, 0, 0), (6080, 2048, 256, 2, 1),
+                                               (16000, 512, 2048, 0, 0), (12345, 4096, 512, 4, 1), (4000, 520, 512, 2, 0)])
+def test_gemm_bf16x3_fp32_grade(lib, M, N, K, epi, c_split):
+    """Split-operand tensor-core GEMM (3 tcgen05 passes over bf16 hi/lo halves): against the fp64 product of the
+    ORIGINAL fp32 operands the error must be fp32-grade -- 3e-5 of the result scale (2^-16 per product, ~100x below the
+    plain bf16 GEMM), and a split output must reproduce the fp32 result to 2^-16 relative."""
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = A.double() @ W.double().t() + b.double()
+    if epi == 1:
+        ref = torch.relu(ref)
+    elif epi == 2:
+        ref = torch.nn.functional.gelu(ref)
+    elif epi == 4:
+        ref = ref[:, 0::2] * torch.nn.functional.gelu(ref[:, 1::2])
+    res = torch.randn(ref.shape, generator=g)
+    use_res = epi == 0 and not c_split
+    if use_res:
+        ref = ref + res.double()
+    No = ref.shape[1]
+    Kp = (K + 7) // 8 * 8
+    ldc = 2 * ((No + 7) // 8 * 8) if c_split else No
+    C = (res.clone().to(DEV) if use_res else
+         torch.zeros(M, ldc, device=DEV, dtype=torch.bfloat16 if c_split else torch.float32))
+    dA, dW, db = _split(A, 2 * Kp).to(DEV), _split(W, 2 * Kp).to(DEV), b.to(DEV)
+    lib.call("pfpp_gemm_bf16x3", dA.data_ptr(), 2 * Kp, dW.data_ptr(), 2 * Kp, db.data_ptr(),
+             C.data_ptr() if use_res else None, No, C.data_ptr(), ldc, c_split, M, N, Kp, epi)
+    torch.cuda.synchronize()
+    out = C.cpu()
+    if c_split:
+        out = out[:, :No].double() + out[:, ldc // 2:ldc // 2 + No].double()
+    err = (out.double() - ref).abs().max().item()
+    tol = 3e-5 * max(1.0, ref.abs().max().item())
+    assert err <= tol, (err, tol)
+
+
+def test_split_bf16_roundtrip(lib):
+    """pfpp_split_bf16: hi + lo reproduces the fp32 value to 2^-16 relative, padding columns are zero."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(777, 148, generator=g) * 3
+    out = torch.full((777, 304), 7.0, dtype=torch.bfloat16, device=DEV)
+    dx = x.to(DEV)
+    lib.call("pfpp_split_bf16", dx.data_ptr(), 777, 148, 148, out.data_ptr(), 304)
+    o = out.cpu().float()
+    assert torch.equal(o[:, :148], x.to(torch.bfloat16).float())
+    assert ((o[:, :148] + o[:, 152:300]) - x).abs().max() <= 2.0 ** -16 * x.abs().max()
+    assert float(o[:, 148:152].abs().sum()) == 0.0 and float(o[:, 300:].abs().sum()) == 0.0
+
+
 def test_vq_matches_oracle(lib, ckpt):
     g = torch.Generator().manual_seed(5)
     cb = ckpt["encoder"]["vector_quantization.embedding.weight"]
