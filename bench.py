@@ -75,7 +75,8 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config-2 measurement of the default run")
-    ap.add_argument("--chunk", type=int, default=32)
+    ap.add_argument("--chunk", type=int, default=320,
+                    help="fragments per pass of the unfused set-abstraction path (fp32 / tc32 modes; ~21 MB of intermediates each)")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll NVML during the timed region")
     ap.add_argument("--no-graph", action="store_true", help="launch every DDPM step eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()
@@ -250,12 +251,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # per-launch event timing of the tensor-core kernels
 # ------------------------------------------------------------------------------------------------
+SEG_SQ = 0  # sum over the probed batch's objects of (valid fragments x latent points)^2
 SA_LEVELS = {1: (32, 0, 64, 64, 128), 2: (64, 128, 128, 128, 256), 3: (64, 256, 256, 256, 512)}  # ns, D, C1, C2, C3
 
 
 def algorithmic_flops(name, args, latent_points=25, head_dim=64):
     """Algorithmic FLOPs (2 per MAC; masked-out work not counted) of one launch, from its C-ABI arguments."""
-    if name == "pfpp_gemm_bf16":
+    if name in ("pfpp_gemm_bf16", "pfpp_gemm_bf16x3"):  # bf16x3: algorithmic FLOPs (the three passes are overhead)
         M, N, K = args[10], args[11], args[12]
         return 2.0 * M * N * K
     if name == "pfpp_gemm_f32":
@@ -269,7 +271,12 @@ def algorithmic_flops(name, args, latent_points=25, head_dim=64):
         M, n_seg, max_len, heads, block = args[1], args[6], args[7], args[8], args[9]
         if block:  # block-diagonal: every token attends to its own block
             return 4.0 * M * block * head_dim * heads
-        return 4.0 * n_seg * max_len * max_len * head_dim * heads  # the bench's segments all have max_len tokens
+        # global attention: every token attends to its object's tokens (sum of squared segment lengths, set by main())
+        return 4.0 * (SEG_SQ or n_seg * max_len * max_len) * head_dim * heads
+    if name == "pfpp_attention_varlen":
+        n_seg, max_len, heads, hd = args[7], args[8], args[9], args[10]
+        sq = n_seg * max_len * max_len if max_len <= latent_points else (SEG_SQ or n_seg * max_len * max_len)
+        return 4.0 * sq * hd * heads
     return 0.0
 
 
@@ -281,8 +288,10 @@ class KernelProbe:
     the same warm engine: a few eagerly launched DDPM steps of the same batch on ONE stream, every probed
     launch bracketed by events on that stream.  Every DDPM step launches the identical kernel sequence."""
 
-    NAMES = ("pfpp_gemm_bf16", "pfpp_gemm_f32", "pfpp_sa_fused", "pfpp_attention_tc", "pfpp_rotate_fps", "pfpp_fps",
-             "pfpp_ball_query", "pfpp_layernorm", "pfpp_vq")
+    NAMES = ("pfpp_gemm_bf16", "pfpp_gemm_bf16x3", "pfpp_gemm_f32", "pfpp_sa_fused", "pfpp_attention_tc",
+             "pfpp_attention_varlen", "pfpp_rotate_fps", "pfpp_fps", "pfpp_ball_query", "pfpp_layernorm", "pfpp_vq",
+             "pfpp_group_gather", "pfpp_group_max", "pfpp_embed_features", "pfpp_combine_embed", "pfpp_mean_pool",
+             "pfpp_ddpm_step")
 
     def __init__(self, lib):
         self.lib = lib
@@ -293,18 +302,18 @@ class KernelProbe:
     def install(self, modules):
         probe = self
 
-        def call(name, *args):
+        def call(name, *args, **kw):
             if probe.enabled and name in probe.NAMES and not torch.cuda.is_current_stream_capturing():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                probe.orig(name, *args)
+                probe.orig(name, *args, **kw)
                 e1.record()
                 key = f"{name}[level {args[0]}]" if name == "pfpp_sa_fused" else name
                 r = probe.rec.setdefault(key, {"events": [], "flops": 0.0})
                 r["events"].append((e0, e1))
                 r["flops"] += algorithmic_flops(name, args)
             else:
-                probe.orig(name, *args)
+                probe.orig(name, *args, **kw)
         self.lib.call = call
         for m in modules:
             m.call = call
@@ -483,8 +492,11 @@ def main():
     # ---- kernel probe: eager DDPM steps of the whole batch on one stream, events around every launch ----
     probe_steps = 3
     eng_p = Engine(arm.ck, num_inference_steps=w["ddpm_steps"], precision=a.precision, device=dev, chunk_frags=a.chunk, max_parts=P)
+    eng_p.coarse = False  # the probe times the individual kernels: sequence them from here, one C call each
     runner = BatchRunner(eng_p, arm.objects, max_iters=1, noise=PerObjectNoise(dev, arm.seeds(0), w["ddpm_steps"]),
                          trajectory=False, use_graph=False)
+    global SEG_SQ
+    SEG_SQ = float(sum((int(o["num_parts"]) * eng_p.L) ** 2 for o in arm.objects))
     runner.begin_iteration()
     runner._launch_step()  # sizes the workspaces
     torch.cuda.synchronize()

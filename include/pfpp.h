@@ -249,6 +249,115 @@ int pfpp_merge(const float* posed, int n_points, int n_comp, int n_clouds, const
  * (denoiser/evaluation/evaluator.py:108,137): out[b,i] = min_j |a[b,i] - b[b,j]|^2. */
 int pfpp_nn_sqdist(const float* a, const float* b, int batches, int N, int M, float* out, cudaStream_t stream);
 
+/* ---- coarse entry points: one call per stage ----------------------------------
+ *
+ * What a C caller binds to run the reference's test_step (test.py:19-43 -> AutoAgglomerative.test_step) without the
+ * Python engine: weights are flat structs of DEVICE pointers (filled once per checkpoint by the host packer,
+ * weights.py -> engine.py), every call sequences this library's kernels over a caller-owned workspace of
+ * pfpp_*_workspace_bytes() bytes, asynchronously on `stream` (capturable in a CUDA graph), with no allocation and
+ * no host synchronisation.  `mode` selects the contraction engine: 0 = fp32 SIMT, 1 = bf16 tcgen05 (fused set
+ * abstraction + tensor-core attention), 2 = bf16x3 split operands on tcgen05 (fp32-grade). */
+#define PFPP_MAX_LAYERS 8
+
+typedef struct PfppLinear {
+  const void* w;     /* [n, k] fp32 (mode 0) | [n, k] bf16 (mode 1) | [n, 2k] bf16 hi/lo split (mode 2); BatchNorm folded */
+  const float* bias; /* [n] or NULL */
+  int n, k;          /* k: the padded K the GEMM runs over (multiple of 4 fp32 / 8 bf16) */
+} PfppLinear;
+
+/* VQVAE.encode (vqvae/model/modules/vq_vae.py:52-68 -> pn2.py:57-68): 3 set-abstraction levels + conv6 + codebook */
+typedef struct PfppEncoderWeights {
+  int mode;
+  int npoint[3], nsample[3];
+  float radius_sq[3];
+  PfppLinear sa[3][3];
+  const void* sa_w0_feat[3]; /* mode 1, fused kernel: layer-0 feature columns [C1, D] bf16 (NULL at level 1) */
+  const float* sa_w0_xyz[3]; /* mode 1, fused kernel: layer-0 centroid-offset columns [C1, 4] fp32 */
+  PfppLinear conv6;
+  const float* codebook; /* [n_codes, 16] */
+  int n_codes, latent_points, latent_dim;
+  int chunk_frags; /* fragments per pass of the unfused path (bounds its [rows, C] intermediates) */
+  int fused_sa;    /* mode 1: use pfpp_sa_fused */
+} PfppEncoderWeights;
+
+typedef struct PfppDenoiserLayer {
+  PfppLinear qkv[2], out[2]; /* [0] = self_attn (block-diagonal), [1] = global_attn (attention.py:75-92) */
+  PfppLinear ff1, ff2;       /* GEGLU rows interleaved (value_j, gate_j) */
+  const float* norm3_w;
+  const float* norm3_b;
+} PfppDenoiserLayer;
+
+/* DenoiserTransformer (denoiser_transformer.py:13-202) + the scheduler's coefficient table */
+typedef struct PfppDenoiserWeights {
+  int mode, C, heads, n_layers, P, L, latent_dim, T;
+  int tc_attention, local_tiles; /* mode 1: tcgen05 attention; 125-token tiles per local-attention CTA */
+  PfppLinear shape_embedding, param_fc;
+  const float* ref_emb; /* [2, C] */
+  const float* pe;      /* [P, C] */
+  const float* mod;     /* [2 * n_layers, T, 2C]: AdaLN rows Linear(SiLU(Embedding[t])) for the T inference timesteps */
+  const float* coef;    /* [T, 5] = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_x, sigma} (pfpp_ddpm_step) */
+  PfppDenoiserLayer layers[PFPP_MAX_LAYERS];
+  PfppLinear head0, head_t2, head_r2, head_t4, head_r4; /* always fp32 */
+} PfppDenoiserWeights;
+
+typedef struct PfppVerifierLayer {
+  PfppLinear qkv, out, l1, l2;
+  const float *n1w, *n1b, *n2w, *n2b;
+} PfppVerifierLayer;
+
+/* VerifierTransformer (verifier_transformer.py:9-65) */
+typedef struct PfppVerifierWeights {
+  int C, heads, n_layers, ffn;
+  int tc; /* 1: projections / FFN as split-operand tcgen05 GEMMs (weights in the mode-2 format), 0: fp32 SIMT */
+  const float *emb_w, *emb_b, *pe, *out_w, *out_b;
+  PfppVerifierLayer layers[PFPP_MAX_LAYERS];
+} PfppVerifierWeights;
+
+/* AutoAgglomerative._apply_rots + _extract_features (auto_aggl.py:70-92) for the F packed fragments frag_slot[f]:
+ * part_pcs [slots,N,3], x [slots,7] pose rows (the quaternion is normalised here) -> z_q [F*L, latent_dim],
+ * xyz [F,L,3], codes [F*L*latent_dim/16] (may be NULL). */
+size_t pfpp_encoder_workspace_bytes(const PfppEncoderWeights* w, int F, int N);
+int pfpp_encoder_forward(const PfppEncoderWeights* w, const float* part_pcs, const int* frag_slot, const float* x, int F,
+                         int N, float* z_q, float* xyz, int* codes, void* workspace, size_t ws_bytes,
+                         cudaStream_t stream);
+
+/* DenoiserTransformer.forward (denoiser_transformer.py:169-202) on the packed batch -> eps [F, 8] (columns 0..6).
+ * frag_step[f] = index of fragment f's timestep in the inference schedule; attention segments over the packed
+ * tokens: per fragment (start f*L, length L) and per object (its valid fragments, <= max_global tokens). */
+size_t pfpp_denoiser_workspace_bytes(const PfppDenoiserWeights* w, int F);
+int pfpp_denoiser_forward(const PfppDenoiserWeights* w, const float* x, const float* scale, const unsigned char* ref,
+                          const int* frag_slot, const int* frag_step, const float* latent, const float* xyz,
+                          const int* frag_seg_start, const int* frag_seg_len, const int* obj_seg_start,
+                          const int* obj_seg_len, int F, int n_obj, int max_global, float* eps, void* workspace,
+                          size_t ws_bytes, cudaStream_t stream);
+
+/* One whole DDPM step of auto_aggl.py:137-151 for the packed batch: step index = *step_counter (device) ->
+ * encoder -> denoiser -> DDPMScheduler.step + reference clamp + history row -> *step_counter += 1.
+ * noise [T, slots, 7] / x_hist [T, slots, 7] (row stride given; x_hist may be NULL); eps_out [F,8] may be NULL. */
+size_t pfpp_step_workspace_bytes(const PfppEncoderWeights* we, const PfppDenoiserWeights* wd, int F, int N);
+int pfpp_denoiser_step(const PfppEncoderWeights* we, const PfppDenoiserWeights* wd, const float* part_pcs, float* x,
+                       const float* scale, const unsigned char* ref, const float* ref_pose, const int* frag_slot,
+                       int* frag_step, int* step_counter, const float* noise, long long noise_step_stride, float* x_hist,
+                       long long hist_step_stride, const int* frag_seg_start, const int* frag_seg_len,
+                       const int* obj_seg_start, const int* obj_seg_len, int F, int n_obj, int max_global, int N,
+                       float* eps_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+/* VerifierTransformer.forward (verifier_transformer.py:42-65) on packed valid-edge tokens (tok_row = dense edge row
+ * b*E + e, tok_i / tok_j = fragment indices, one segment per object) -> logits [n_rows] (zero on invalid rows). */
+size_t pfpp_verifier_workspace_bytes(const PfppVerifierWeights* w, int n_tokens);
+int pfpp_verifier_forward(const PfppVerifierWeights* w, const float* feat, const int* tok_row, const int* tok_i,
+                          const int* tok_j, int n_tokens, const int* seg_start, const int* seg_len, int n_segments,
+                          int max_len, long long n_rows, float* logits, void* workspace, size_t ws_bytes,
+                          cudaStream_t stream);
+
+/* sizeof of the structs above as compiled into the library (which: 0 PfppLinear, 1 PfppEncoderWeights,
+ * 2 PfppDenoiserLayer, 3 PfppDenoiserWeights, 4 PfppVerifierLayer, 5 PfppVerifierWeights; 0 for anything else). */
+size_t pfpp_struct_bytes(int which);
+
+/* Hash of the sources this library was built from (build.py: FNV-1a 64 of csrc + this header), so a caller can
+ * tie the loaded binary to a source tree. */
+unsigned long long pfpp_build_id(void);
+
 /* ---- Chamfer distance with gradients ----------------------------------- */
 
 /* chamfer_cuda.chamfer_forward (Jigsaw_matching/utils/chamfer/cuda/chamfer_kernel.cu:31-173): nearest neighbour of

@@ -52,13 +52,58 @@ SIGNATURES = {
     "pfpp_verifier_head": [_P, _P, _I, _P, _P, _I, _P, _P],
     "pfpp_merge_filter": [_P, _I, _I, _I, _F, _P, _P, _P],
     "pfpp_nn_sqdist": [_P, _P, _I, _I, _I, _P, _P],
+    "pfpp_encoder_forward": [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, ctypes.c_size_t, _P],
+    "pfpp_denoiser_forward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, ctypes.c_size_t, _P],
+    "pfpp_denoiser_step": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P,
+                           ctypes.c_size_t, _P],
+    "pfpp_verifier_forward": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _L, _P, _P, ctypes.c_size_t, _P],
     "pfpp_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "pfpp_chamfer_backward": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
     "pfpp_merge": [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                    ctypes.c_size_t, _P],
 }
 # entry points that return a size instead of a status (no stream argument)
-SIZE_FUNCS = {"pfpp_merge_workspace_bytes": [_I, _I, _I]}
+SIZE_FUNCS = {"pfpp_merge_workspace_bytes": [_I, _I, _I], "pfpp_encoder_workspace_bytes": [_P, _I, _I],
+              "pfpp_denoiser_workspace_bytes": [_P, _I], "pfpp_step_workspace_bytes": [_P, _P, _I, _I],
+              "pfpp_verifier_workspace_bytes": [_P, _I], "pfpp_struct_bytes": [_I]}
+
+# ---- flat weight structs of the coarse entry points (mirror include/pfpp.h field for field) ----
+MAX_LAYERS = 8
+
+
+class PfppLinear(ctypes.Structure):
+    _fields_ = [("w", _P), ("bias", _P), ("n", _I), ("k", _I)]
+
+
+class PfppEncoderWeights(ctypes.Structure):
+    _fields_ = [("mode", _I), ("npoint", _I * 3), ("nsample", _I * 3), ("radius_sq", _F * 3),
+                ("sa", (PfppLinear * 3) * 3), ("sa_w0_feat", _P * 3), ("sa_w0_xyz", _P * 3), ("conv6", PfppLinear),
+                ("codebook", _P), ("n_codes", _I), ("latent_points", _I), ("latent_dim", _I), ("chunk_frags", _I),
+                ("fused_sa", _I)]
+
+
+class PfppDenoiserLayer(ctypes.Structure):
+    _fields_ = [("qkv", PfppLinear * 2), ("out", PfppLinear * 2), ("ff1", PfppLinear), ("ff2", PfppLinear),
+                ("norm3_w", _P), ("norm3_b", _P)]
+
+
+class PfppDenoiserWeights(ctypes.Structure):
+    _fields_ = [("mode", _I), ("C", _I), ("heads", _I), ("n_layers", _I), ("P", _I), ("L", _I), ("latent_dim", _I),
+                ("T", _I), ("tc_attention", _I), ("local_tiles", _I), ("shape_embedding", PfppLinear),
+                ("param_fc", PfppLinear), ("ref_emb", _P), ("pe", _P), ("mod", _P), ("coef", _P),
+                ("layers", PfppDenoiserLayer * MAX_LAYERS), ("head0", PfppLinear), ("head_t2", PfppLinear),
+                ("head_r2", PfppLinear), ("head_t4", PfppLinear), ("head_r4", PfppLinear)]
+
+
+class PfppVerifierLayer(ctypes.Structure):
+    _fields_ = [("qkv", PfppLinear), ("out", PfppLinear), ("l1", PfppLinear), ("l2", PfppLinear), ("n1w", _P),
+                ("n1b", _P), ("n2w", _P), ("n2b", _P)]
+
+
+class PfppVerifierWeights(ctypes.Structure):
+    _fields_ = [("C", _I), ("heads", _I), ("n_layers", _I), ("ffn", _I), ("tc", _I), ("emb_w", _P), ("emb_b", _P),
+                ("pe", _P), ("out_w", _P), ("out_b", _P), ("layers", PfppVerifierLayer * MAX_LAYERS)]
+
 
 _lib = None
 
@@ -85,6 +130,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = ctypes.c_size_t
+    lib.pfpp_build_id.argtypes = []
+    lib.pfpp_build_id.restype = ctypes.c_ulonglong
     _lib = lib
     return lib
 
@@ -103,12 +150,13 @@ def stream():
 launch_count = 0
 
 
-def call(name, *args):
-    """Invoke an entry point on torch's current stream; raise on a non-zero status."""
+def call(name, *args, kernels=1):
+    """Invoke an entry point on torch's current stream; raise on a non-zero status.  `kernels` = the number of
+    kernels the call launches (the coarse entry points launch whole sequences), for bench.py's gpu_launches."""
     global launch_count
     lib = load()
     rc = getattr(lib, name)(*args, stream())
-    launch_count += 1
+    launch_count += kernels
     if rc != 0:
         kind = "argument error" if rc < 0 else "cudaError_t"
         raise PfppError("%s failed: %s %d" % (name, kind, rc))

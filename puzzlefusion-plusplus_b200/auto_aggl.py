@@ -76,45 +76,32 @@ class VerifierTransformer(_WeightHolder):
         return self._owner[0]._verifier_forward(edge_features, edge_indices, mask)
 
 
-class AutoAgglomerative(_Base):
-    def __init__(self, cfg):
-        super().__init__()
-        self.cfg = cfg
-        m = cfg.denoiser.model
-        P = int(cfg.denoiser.get("data", {}).get("max_num_part", 20)) if hasattr(cfg.denoiser, "get") else 20
-        self.max_parts = P
-        self.denoiser = DenoiserTransformer(synthetic.make_denoiser_state(0, C=m.embed_dim, layers=m.num_layers,
-                                                                        max_parts=P), self, "denoiser")
-        self.verifier = VerifierTransformer(synthetic.make_verifier_state(2, C=cfg.verifier.model.embed_dim,
-                                                                        layers=cfg.verifier.model.num_layers,
-                                                                        max_parts=P), self, "verifier")
-        self.encoder = VQVAE(synthetic.make_encoder_state(1), self, "encoder")
-        self.noise_scheduler = PiecewiseScheduler(
-            num_train_timesteps=m.DDPM_TRAIN_STEPS, beta_schedule=m.DDPM_BETA_SCHEDULE, prediction_type=m.PREDICT_TYPE,
-            beta_start=m.BETA_START, beta_end=m.BETA_END, clip_sample=False, timestep_spacing=m.timestep_spacing)
-        self.noise_scheduler.set_timesteps(num_inference_steps=m.num_inference_steps)
-        self.num_points, self.num_channels = m.num_point, m.num_dim
-        self.rmse_r_list, self.rmse_t_list, self.acc_list, self.cd_list = [], [], [], []
-        ext = cfg.get("pfpp", {}) if hasattr(cfg, "get") else {}
-        self.precision = ext.get("precision", "bf16")
-        self.chunk_frags = ext.get("chunk_frags", 32)
-        self._engine = None
+class _EngineOwner(_Base):
+    """Shared by the drop-in LightningModules: weight-holder sub-modules + the Engine built from them on first use."""
+    _engine = None
+    precision = "bf16"
+    chunk_frags = 320
+    max_parts = 20
 
-    # ---- engine management ------------------------------------------------------------------
+    def _model_cfg(self):
+        """(denoiser model cfg, verifier layer count or None)"""
+        raise NotImplementedError
+
     def _invalidate(self):
         self._engine = None
 
     @property
     def engine(self):
         if self._engine is None:
-            ck = {"denoiser": self.denoiser.state_dict(), "encoder": self.encoder.state_dict(),
-                  "verifier": self.verifier.state_dict()}
-            m = self.cfg.denoiser.model
+            m, ver_layers = self._model_cfg()
+            ck = {"denoiser": self.denoiser.state_dict(), "encoder": self.encoder.state_dict()}
+            if ver_layers is not None:
+                ck["verifier"] = self.verifier.state_dict()
             dev = torch.device("cuda", torch.cuda.current_device())
             self._engine = Engine(ck, num_inference_steps=m.num_inference_steps, precision=self.precision, device=dev,
                                   num_layers=m.num_layers, heads=m.num_heads, max_parts=self.max_parts,
                                   latent_points=m.num_point, latent_dim=m.num_dim,
-                                  verifier_layers=self.cfg.verifier.model.num_layers, chunk_frags=self.chunk_frags)
+                                  verifier_layers=ver_layers or 6, chunk_frags=self.chunk_frags)
         return self._engine
 
     # ---- module-level surfaces ----------------------------------------------------------------
@@ -134,8 +121,12 @@ class AutoAgglomerative(_Base):
         B, P, L, _ = latent.shape
         valid = (part_valids.reshape(-1) > 0).cpu()
         slots = torch.nonzero(valid).reshape(-1).to(torch.int32)
-        ts = [int(t) for t in e.sched.timesteps]
-        tidx = torch.tensor([ts.index(int(timesteps[int(s) // P])) for s in slots], dtype=torch.int32)
+        # AdaLN rows are tabulated for every training timestep on first use (any timestep is accepted, as in the
+        # reference's forward): the per-fragment index is the timestep value itself
+        th = timesteps.detach().cpu().long().reshape(-1)
+        if int(th.min()) < 0 or int(th.max()) >= e.sched.num_train_timesteps:
+            raise ValueError("timesteps must lie in [0, num_train_timesteps)")
+        tidx = torch.tensor([int(th[int(s) // P]) for s in slots], dtype=torch.int32)
         dv = lambda t: t.to(e.device, torch.float32).contiguous()  # noqa: E731
         F = slots.numel()
         lat = dv(latent.reshape(B * P, L, -1))[valid.to(e.device)].reshape(F * L, -1).contiguous()
@@ -145,7 +136,7 @@ class AutoAgglomerative(_Base):
         seg_local, seg_global, max_global = _seg_tensors(e, counts)
         eps = e.denoise_eps(dv(x.reshape(B * P, 7)), dv(scale.reshape(B * P)),
                             ref_part.reshape(B * P).to(e.device).to(torch.uint8).contiguous(), slots.to(e.device),
-                            tidx.to(e.device), lat, xz, seg_local, seg_global, max_global)
+                            tidx.to(e.device), lat, xz, seg_local, seg_global, max_global, any_timestep=True)
         out = torch.zeros(B * P, 7, device=e.device)
         out[slots.to(e.device).long()] = eps[:, :7]
         return out.view(B, P, 7)
@@ -168,6 +159,34 @@ class AutoAgglomerative(_Base):
         feat = edge_features.to(e.device, torch.float32).reshape(B * E, 7).contiguous()
         logits = e.verifier_logits(feat, a, b_, c, d, f, max(seg_len), B * E)
         return logits.view(B, E, 1).clone()
+
+
+class AutoAgglomerative(_EngineOwner):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        m = cfg.denoiser.model
+        P = int(cfg.denoiser.get("data", {}).get("max_num_part", 20)) if hasattr(cfg.denoiser, "get") else 20
+        self.max_parts = P
+        self.denoiser = DenoiserTransformer(synthetic.make_denoiser_state(0, C=m.embed_dim, layers=m.num_layers,
+                                                                        max_parts=P), self, "denoiser")
+        self.verifier = VerifierTransformer(synthetic.make_verifier_state(2, C=cfg.verifier.model.embed_dim,
+                                                                        layers=cfg.verifier.model.num_layers,
+                                                                        max_parts=P), self, "verifier")
+        self.encoder = VQVAE(synthetic.make_encoder_state(1), self, "encoder")
+        self.noise_scheduler = PiecewiseScheduler(
+            num_train_timesteps=m.DDPM_TRAIN_STEPS, beta_schedule=m.DDPM_BETA_SCHEDULE, prediction_type=m.PREDICT_TYPE,
+            beta_start=m.BETA_START, beta_end=m.BETA_END, clip_sample=False, timestep_spacing=m.timestep_spacing)
+        self.noise_scheduler.set_timesteps(num_inference_steps=m.num_inference_steps)
+        self.num_points, self.num_channels = m.num_point, m.num_dim
+        self.rmse_r_list, self.rmse_t_list, self.acc_list, self.cd_list = [], [], [], []
+        ext = cfg.get("pfpp", {}) if hasattr(cfg, "get") else {}
+        self.precision = ext.get("precision", "bf16")
+        self.chunk_frags = ext.get("chunk_frags", 320)
+        self._engine = None
+
+    def _model_cfg(self):
+        return self.cfg.denoiser.model, self.cfg.verifier.model.num_layers
 
     # ---- the hot loop ------------------------------------------------------------------------
     @staticmethod
@@ -225,6 +244,109 @@ class AutoAgglomerative(_Base):
                 f.write(str(o["mesh_file_path"]))
 
     def on_test_epoch_end(self):
+        tot = [torch.mean(torch.cat(v)) for v in (self.acc_list, self.rmse_t_list, self.rmse_r_list, self.cd_list)]
+        if hasattr(self, "log") and _Base is not nn.Module:
+            for name, v in zip(("eval/part_acc", "eval/rmse_t", "eval/rmse_r", "eval/shape_cd"), tot):
+                self.log(name, v, sync_dist=True)
+        self.acc_list, self.rmse_t_list, self.rmse_r_list, self.cd_list = [], [], [], []
+        return tuple(tot)
+
+
+class Denoiser(_EngineOwner):
+    """Drop-in for the reference's ``Denoiser`` LightningModule (puzzlefusion_plusplus/denoiser/model/denoiser.py),
+    inference side: ``forward`` (the noise-prediction forward of training / validation,
+    :80-113, any training timestep), ``_loss`` (:116-125), ``validation_step`` (:153-216: validation loss + the
+    T-step sampling loop + the four evaluation metrics) and ``on_validation_epoch_end`` (:219-234).  ``cfg`` is the
+    composed denoiser config (``cfg.model.*``), i.e. ``config.compose(...).denoiser``.  There is no backward pass:
+    ``training_step`` raises (training is out of scope)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        m = cfg.model
+        P = int(cfg.get("data", {}).get("max_num_part", 20)) if hasattr(cfg, "get") else 20
+        self.max_parts = P
+        self.denoiser = DenoiserTransformer(synthetic.make_denoiser_state(0, C=m.embed_dim, layers=m.num_layers,
+                                                                        max_parts=P), self, "denoiser")
+        self.encoder = VQVAE(synthetic.make_encoder_state(1), self, "encoder")
+        self.noise_scheduler = PiecewiseScheduler(
+            num_train_timesteps=m.DDPM_TRAIN_STEPS, beta_schedule=m.DDPM_BETA_SCHEDULE, prediction_type=m.PREDICT_TYPE,
+            beta_start=m.BETA_START, beta_end=m.BETA_END, clip_sample=False, timestep_spacing=m.timestep_spacing)
+        self.noise_scheduler.set_timesteps(num_inference_steps=m.num_inference_steps)
+        self.num_points, self.num_channels = m.num_point, m.num_dim
+        self.rmse_r_list, self.rmse_t_list, self.acc_list, self.cd_list = [], [], [], []
+        self.val_losses = []
+        ext = cfg.get("pfpp", {}) if hasattr(cfg, "get") else {}
+        self.precision = ext.get("precision", "bf16")
+        self._engine = None
+
+    def _model_cfg(self):
+        return self.cfg.model, None
+
+    def _extract_features(self, part_pcs, part_valids, noisy):
+        """denoiser.py:66-77: rotate by the noisy quaternion, encode the valid fragments, scatter into zero-padded
+        latent [B,P,L,64] / xyz [B,P,L,3]."""
+        e = self.engine
+        B, P, N, _ = part_pcs.shape
+        valid = (part_valids.reshape(-1) > 0).to(e.device)
+        slots = torch.nonzero(valid).reshape(-1).to(torch.int32)
+        pcs = part_pcs.reshape(B * P, N, 3).to(e.device, torch.float32).contiguous()
+        x = noisy.reshape(B * P, 7).to(e.device, torch.float32).contiguous()
+        lat, xyz = e.encode(pcs, slots, x, N)
+        latent = torch.zeros(B * P, e.L, e.latent_dim, device=e.device)
+        xyz_out = torch.zeros(B * P, e.L, 3, device=e.device)
+        latent[slots.long()] = lat.view(-1, e.L, e.latent_dim)
+        xyz_out[slots.long()] = xyz
+        return latent.view(B, P, e.L, -1), xyz_out.view(B, P, e.L, 3)
+
+    @torch.no_grad()
+    def forward(self, data_dict, noise=None, timesteps=None):
+        """denoiser.py:80-113.  ``noise`` / ``timesteps`` may be passed in (tests); by default they are drawn on the
+        device with the reference's calls in the reference's order (randn, then randint)."""
+        dev = self.engine.device
+        gt = torch.cat([data_dict["part_trans"], data_dict["part_rots"]], dim=-1).to(dev, torch.float32)
+        ref_part = data_dict["ref_part"].to(dev).bool()
+        if noise is None:
+            noise = torch.randn(gt.shape, device=dev)
+        if timesteps is None:
+            timesteps = torch.randint(0, self.noise_scheduler.num_train_timesteps, (gt.shape[0],), device=dev).long()
+        noise, timesteps = noise.to(dev), timesteps.to(dev)
+        noisy = self.noise_scheduler.add_noise(gt, noise, timesteps)
+        noisy[ref_part] = gt[ref_part]
+        latent, xyz = self._extract_features(data_dict["part_pcs"], data_dict["part_valids"], noisy)
+        pred = self.denoiser(noisy, timesteps, latent, xyz, data_dict["part_valids"], data_dict["part_scale"], ref_part)
+        return {"pred_noise": pred, "gt_noise": noise}
+
+    def _loss(self, data_dict, output_dict):
+        """denoiser.py:116-125: MSE over valid, non-reference fragments."""
+        dev = output_dict["pred_noise"].device
+        valid = data_dict["part_valids"].to(dev).bool().clone()
+        valid[data_dict["ref_part"].to(dev).bool()] = False
+        return {"mse_loss": torch.nn.functional.mse_loss(output_dict["pred_noise"][valid], output_dict["gt_noise"][valid])}
+
+    def training_step(self, data_dict, idx):
+        raise NotImplementedError("pfpp-b200 implements the inference / validation side only (no backward kernels)")
+
+    @torch.no_grad()
+    def validation_step(self, data_dict, idx):
+        """denoiser.py:153-216."""
+        out = self(data_dict)
+        loss = self._loss(data_dict, out)
+        self.val_losses.append(loss["mse_loss"].detach().reshape(1).cpu())
+        if hasattr(self, "log") and _Base is not nn.Module:
+            self.log("val_loss/mse_loss", loss["mse_loss"], on_step=False, on_epoch=True)
+            self.log("val_loss/total_loss", loss["mse_loss"], on_step=False, on_epoch=True)
+        objs = AutoAgglomerative._split(data_dict)
+        e = self.engine
+        res = run_batch(e, objs, max_iters=1, noise=GlobalTorchNoise(e.device), trajectory=False)
+        m = object_metrics(res, objs, e.device, engine=e).cpu()
+        self.acc_list.append(m[:, 0])
+        self.rmse_r_list.append(m[:, 1])
+        self.rmse_t_list.append(m[:, 2])
+        self.cd_list.append(m[:, 3])
+        return res
+
+    def on_validation_epoch_end(self):
         tot = [torch.mean(torch.cat(v)) for v in (self.acc_list, self.rmse_t_list, self.rmse_r_list, self.cd_list)]
         if hasattr(self, "log") and _Base is not nn.Module:
             for name, v in zip(("eval/part_acc", "eval/rmse_t", "eval/rmse_r", "eval/shape_cd"), tot):

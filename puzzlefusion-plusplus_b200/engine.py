@@ -21,6 +21,7 @@ engine:
            error 2^-16 per product instead of bf16's 2^-8), activations travel between kernels as hi/lo pairs, softmax
            attention stays fp32 SIMT.  The verifier uses the same split GEMMs in "bf16" and "tc32" modes.
 """
+import ctypes
 import gc
 
 import numpy as np
@@ -44,7 +45,7 @@ class Engine:
     _FUSED_LEVELS = {(32, 0, 64, 64, 128): 1, (64, 128, 128, 128, 256): 2, (64, 256, 256, 256, 512): 3}
 
     def __init__(self, ckpt, num_inference_steps=20, precision="bf16", device="cuda:0", num_layers=6, heads=8,
-                 max_parts=20, latent_points=25, latent_dim=64, verifier_layers=6, sa_cfg=SA_CFG, chunk_frags=32,
+                 max_parts=20, latent_points=25, latent_dim=64, verifier_layers=6, sa_cfg=SA_CFG, chunk_frags=320,
                  freeze_gc=False):
         if not torch.cuda.is_available():
             raise _lib.PfppError("pfpp-b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -77,8 +78,10 @@ class Engine:
         self.tc_attention = True  # tcgen05 attention in bf16 mode (segments > 512 tokens stream K/V through a ring)
         self.fused_sa = True     # fused gather + 3-layer MLP + max tcgen05 kernel in bf16 mode
         self.local_tiles = 4     # 125-token tiles (5 fragments) per local-attention CTA, two per softmax group
+        self.coarse = True       # run the stages through the coarse C entry points (pfpp_encoder_forward, ...)
         self._ws = {}
         self._ws_version = 0
+        self._build_weight_structs()
         self._step_ctx = {}  # loop.StepContext cache: persistent step buffers + captured graph per batch geometry
         if freeze_gc:
             # Opt-in, process-wide: move everything allocated so far (checkpoints, packed weights, objects) into the
@@ -86,6 +89,78 @@ class Engine:
             # the agglomeration loop, do not re-traverse them -- measured ~100 ms pauses per batch of 32 objects.
             gc.collect()
             gc.freeze()
+
+    # ------------------------------------------------------------------ flat weight structs of the coarse C ABI
+    def _lin(self, lin, mode):
+        if lin is None:
+            return _lib.PfppLinear()
+        w, k = ((lin.w16s, lin.k16) if mode == 2 else (lin.w16, lin.k16) if mode == 1 else (lin.w32, lin.k32))
+        return _lib.PfppLinear(w.data_ptr(), _lib.ptr(lin.b), lin.n, k)
+
+    def _build_weight_structs(self):
+        """PfppEncoderWeights / PfppDenoiserWeights / PfppVerifierWeights (include/pfpp.h): device pointers into the
+        packed weights this engine keeps alive."""
+        m = self.mode
+        we = _lib.PfppEncoderWeights()
+        we.mode = m
+        for i, (S, radius, ns) in enumerate(self.sa_cfg):
+            we.npoint[i], we.nsample[i] = S, ns
+            we.radius_sq[i] = float(np.float32(radius ** 2))
+            for j in range(3):
+                we.sa[i][j] = self._lin(self.enc.sa[i][j], m)
+            l0 = self.enc.sa[i][0]
+            we.sa_w0_feat[i] = _lib.ptr(getattr(l0, "w16_feat", None))
+            we.sa_w0_xyz[i] = _lib.ptr(getattr(l0, "wxyz", None))
+        we.conv6 = self._lin(self.enc.conv6, m)
+        we.codebook = self.enc.codebook.data_ptr()
+        we.n_codes, we.latent_points, we.latent_dim = self.enc.codebook.shape[0], self.L, self.latent_dim
+        we.chunk_frags, we.fused_sa = self.chunk, int(self.fused_sa)
+        self.cw_enc = we
+        w = self.den
+        if len(w.layers) > _lib.MAX_LAYERS:
+            raise ValueError("more denoiser layers than PFPP_MAX_LAYERS")
+        wd = _lib.PfppDenoiserWeights()
+        wd.mode, wd.C, wd.heads, wd.n_layers, wd.P, wd.L = m, self.C, self.heads, len(w.layers), self.P, self.L
+        wd.latent_dim, wd.T = self.latent_dim, self.T
+        wd.tc_attention, wd.local_tiles = int(self.tc_attention), self.local_tiles
+        wd.shape_embedding, wd.param_fc = self._lin(w.shape_embedding, m), self._lin(w.param_fc, m)
+        wd.ref_emb, wd.pe, wd.mod, wd.coef = w.ref_emb.data_ptr(), w.pe.data_ptr(), w.mod.data_ptr(), self.coef.data_ptr()
+        for i, lw in enumerate(w.layers):
+            L = wd.layers[i]
+            for j, name in enumerate(("self_attn", "global_attn")):
+                L.qkv[j], L.out[j] = self._lin(lw[name + ".qkv"], m), self._lin(lw[name + ".out"], m)
+            L.ff1, L.ff2 = self._lin(lw["ff1"], m), self._lin(lw["ff2"], m)
+            L.norm3_w, L.norm3_b = lw["norm3.w"].data_ptr(), lw["norm3.b"].data_ptr()
+        for name in ("head0", "head_t2", "head_r2", "head_t4", "head_r4"):
+            setattr(wd, name, self._lin(getattr(w, name), 0))
+        self.cw_den = wd
+        self.cw_ver = None
+        if self.ver is not None:
+            v = self.ver
+            wv = _lib.PfppVerifierWeights()
+            wv.C, wv.heads, wv.n_layers, wv.ffn, wv.tc = v.C, self.heads, len(v.layers), v.layers[0]["l1"].n, int(self.verifier_tc)
+            wv.emb_w, wv.emb_b, wv.pe = v.emb_w.data_ptr(), v.emb_b.data_ptr(), v.pe.data_ptr()
+            wv.out_w, wv.out_b = v.out_w.data_ptr(), v.out_b.data_ptr()
+            vm = 2 if self.verifier_tc else 0
+            for i, lw in enumerate(v.layers):
+                L = wv.layers[i]
+                L.qkv, L.out, L.l1, L.l2 = (self._lin(lw[k], vm) for k in ("qkv", "out", "l1", "l2"))
+                L.n1w, L.n1b, L.n2w, L.n2b = (lw[k].data_ptr() for k in ("n1w", "n1b", "n2w", "n2b"))
+            self.cw_ver = wv
+
+    def _sync_switches(self):
+        """the kernel-selection switches may be flipped between calls (tests, tools): mirror them into the structs"""
+        self.cw_enc.fused_sa = int(self.fused_sa)
+        self.cw_den.tc_attention, self.cw_den.local_tiles = int(self.tc_attention), self.local_tiles
+
+    def step_kernels(self, F):
+        """kernels one DDPM step launches (bench.py's gpu_launches; the coarse entry points launch whole sequences)"""
+        fused = self.bf16 and self.fused_sa
+        chunks = 1 if fused else -(-F // min(self.chunk, max(F, 1)))
+        enc = chunks * (3 * (3 if fused else 7) + 1) + 1
+        tc_local = self.bf16 and self.tc_attention
+        den = 4 + int(tc_local) + len(self.den.layers) * 11 + 6
+        return 3 + enc + den
 
     # ------------------------------------------------------------------ helpers
     def buf(self, name, shape, dtype):
@@ -199,6 +274,15 @@ class Engine:
         """part_pcs [slots,N,3], frag_slot int32 [F], x [slots,7] -> latent [F*L,64] fp32, xyz [F,L,3] fp32."""
         F = frag_slot.numel()
         L, act, bf, wm = self.L, self.act_dtype, self.mode, self.wm
+        if self.coarse and trace is None:
+            self._sync_switches()
+            latent = self.buf("latent", (F * L, self.latent_dim), torch.float32)
+            xyz_out = self.buf("xyz3", (F, L, 3), torch.float32)
+            n = int(_lib.load().pfpp_encoder_workspace_bytes(ctypes.byref(self.cw_enc), F, N))
+            ws = self.buf("enc_ws", (n,), torch.uint8)
+            call("pfpp_encoder_forward", ctypes.byref(self.cw_enc), part_pcs.data_ptr(), frag_slot.data_ptr(), x.data_ptr(), F,
+                 N, latent.data_ptr(), xyz_out.data_ptr(), None, ws.data_ptr(), n)
+            return latent, xyz_out
         z_e = self.buf("z_e", (F * L, self.latent_dim), torch.float32)
         xyz_out = self.buf("xyz3", (F, L, 3), torch.float32)
         latent = self.buf("latent", (F * L, self.latent_dim), torch.float32)
@@ -281,10 +365,34 @@ class Engine:
 
     # ------------------------------------------------------------------ denoiser
     def denoise_eps(self, x, scale, ref, frag_slot, frag_tidx, latent, xyz, seg_local, seg_global, max_global,
-                    trace=None):
-        """One DenoiserTransformer forward on the packed batch -> eps [F, 8] fp32 (cols 0..6 used)."""
+                    trace=None, any_timestep=False):
+        """One DenoiserTransformer forward on the packed batch -> eps [F, 8] fp32 (cols 0..6 used).
+
+        frag_tidx[f] indexes the inference schedule (step number); with any_timestep it is the timestep value itself
+        (AdaLN rows come from the table of all training timesteps, DenoiserWeights.mod_all)."""
+        if any_timestep:
+            # same launch sequence over the all-timesteps AdaLN table: swap the table for this call
+            n_train = self.sched.num_train_timesteps
+            saved = (self.den.mod, self.cw_den.mod, self.cw_den.T)
+            self.den.mod = self.den.mod_all(n_train)
+            self.cw_den.mod, self.cw_den.T = self.den.mod.data_ptr(), n_train
+            try:
+                return self.denoise_eps(x, scale, ref, frag_slot, frag_tidx, latent, xyz, seg_local, seg_global, max_global,
+                                        trace)
+            finally:
+                self.den.mod, self.cw_den.mod, self.cw_den.T = saved
         F = frag_slot.numel()
         L, C, H, act, bf, wm = self.L, self.C, self.heads, self.act_dtype, self.mode, self.wm
+        if self.coarse and trace is None:
+            self._sync_switches()
+            eps = self.buf("eps", (F, 8), torch.float32)
+            n = int(_lib.load().pfpp_denoiser_workspace_bytes(ctypes.byref(self.cw_den), F))
+            ws = self.buf("den_ws", (n,), torch.uint8)
+            call("pfpp_denoiser_forward", ctypes.byref(self.cw_den), x.data_ptr(), scale.data_ptr(), ref.data_ptr(),
+                 frag_slot.data_ptr(), frag_tidx.data_ptr(), latent.data_ptr(), xyz.data_ptr(), seg_local[0].data_ptr(),
+                 seg_local[1].data_ptr(), seg_global[0].data_ptr(), seg_global[1].data_ptr(), F, seg_global[0].numel(),
+                 max_global, eps.data_ptr(), ws.data_ptr(), n)
+            return eps
         M = F * L
         D = C // H
         w = self.den
@@ -349,6 +457,21 @@ class Engine:
         self.gemm(hr, C // 2, w.head_r4, eps[:, 3:], 8, F, EPI_NONE, force_f32=True)
         return eps
 
+    # ------------------------------------------------------------------ one whole DDPM step (coarse C ABI)
+    def ddpm_step(self, part_pcs, x, scale, ref, ref_pose, frag_slot, frag_step, step_ctr, noise_all, hist, seg_local,
+                  seg_global, max_global, N):
+        """auto_aggl.py:137-151 for the packed batch in ONE C call (pfpp_denoiser_step): step-counter broadcast,
+        encoder, denoiser, scheduler step + reference clamp + history row, counter advance."""
+        self._sync_switches()
+        F = frag_slot.numel()
+        n = int(_lib.load().pfpp_step_workspace_bytes(ctypes.byref(self.cw_enc), ctypes.byref(self.cw_den), F, N))
+        ws = self.buf("step_ws", (n,), torch.uint8)
+        call("pfpp_denoiser_step", ctypes.byref(self.cw_enc), ctypes.byref(self.cw_den), part_pcs.data_ptr(), x.data_ptr(),
+             scale.data_ptr(), ref.data_ptr(), ref_pose.data_ptr(), frag_slot.data_ptr(), frag_step.data_ptr(),
+             step_ctr.data_ptr(), noise_all.data_ptr(), noise_all.stride(0), hist.data_ptr(), hist.stride(0),
+             seg_local[0].data_ptr(), seg_local[1].data_ptr(), seg_global[0].data_ptr(), seg_global[1].data_ptr(), F,
+             seg_global[0].numel(), max_global, N, None, ws.data_ptr(), n, kernels=self.step_kernels(F))
+
     # ------------------------------------------------------------------ verifier
     def verifier_logits(self, feat, tok_row, tok_i, tok_j, seg_start, seg_len, max_len, n_rows):
         """feat [n_rows,7] fp32 dense edge features; packed valid-edge tokens -> logits [n_rows] fp32.
@@ -359,6 +482,15 @@ class Engine:
         w = self.ver
         C, H = w.C, self.heads
         n = tok_row.numel()
+        if self.coarse:
+            self.cw_ver.tc = int(self.verifier_tc)
+            logits = self.buf("v_logits", (n_rows,), torch.float32)
+            nb = int(_lib.load().pfpp_verifier_workspace_bytes(ctypes.byref(self.cw_ver), n))
+            ws = self.buf("ver_ws", (nb,), torch.uint8)
+            call("pfpp_verifier_forward", ctypes.byref(self.cw_ver), feat.data_ptr(), tok_row.data_ptr(), tok_i.data_ptr(),
+                 tok_j.data_ptr(), n, seg_start.data_ptr(), seg_len.data_ptr(), seg_start.numel(), max_len, n_rows,
+                 logits.data_ptr(), ws.data_ptr(), nb)
+            return logits
         tc = self.verifier_tc
         ffn = w.layers[0]["l1"].n
         h = self.buf("v_h", (n, C), torch.float32)

@@ -223,7 +223,7 @@ class StepContext:
     def get(e, slots, N, F, n_obj, max_global):
         # the launch sequence also depends on the engine's kernel-selection switches: part of the key, so that a
         # graph captured under other settings is never replayed
-        key = (slots, N, F, n_obj, max_global, e.T, e.fused_sa, e.tc_attention, e.local_tiles)
+        key = (slots, N, F, n_obj, max_global, e.T, e.fused_sa, e.tc_attention, e.local_tiles, e.coarse)
         cache = e._step_ctx
         ctx = cache.pop(key, None)
         if ctx is None:
@@ -347,6 +347,11 @@ class BatchRunner:
 
     def _launch_step(self):
         st, e = self.st, self.e
+        if e.coarse and self.record is None:
+            # the whole step is one C call (pfpp_denoiser_step)
+            e.ddpm_step(self.pcs, self.x, self.scale_dev, self.ref_dev, self.ref_pose, self.frag_slot, self.frag_step,
+                        self.step_ctr, self.noise_all, self.hist, self.seg_local, self.seg_global, self.max_global, st.N)
+            return None
         call("pfpp_step_broadcast", self.step_ctr.data_ptr(), self.frag_step.data_ptr(), self.F)
         latent, xyz = e.encode(self.pcs, self.frag_slot, self.x, st.N)
         eps = e.denoise_eps(self.x, self.scale_dev, self.ref_dev, self.frag_slot, self.frag_step, latent, xyz, self.seg_local,

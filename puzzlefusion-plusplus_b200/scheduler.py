@@ -65,6 +65,17 @@ class PiecewiseScheduler:
     def coefficient_table(self):
         return torch.stack([self.coefficients(t) for t in self.timesteps])  # [T, 5]
 
+    def add_noise(self, original_samples, noise, timesteps):
+        """diffusers DDPMScheduler.add_noise (training / validation forward, denoiser.py:91):
+        sqrt(abar_t) x0 + sqrt(1 - abar_t) noise with t per leading batch index."""
+        ac = self.alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)
+        t = timesteps.to(original_samples.device)
+        a = (ac[t] ** 0.5).flatten()
+        b = ((1 - ac[t]) ** 0.5).flatten()
+        while a.dim() < original_samples.dim():
+            a, b = a.unsqueeze(-1), b.unsqueeze(-1)
+        return a * original_samples + b * noise
+
     def step(self, model_output, timestep, sample, generator=None):
         """API-compatible single step on CUDA tensors of shape [..., 7] (draws its own noise, t > 0)."""
         t = int(timestep)

@@ -88,7 +88,6 @@ class DenoiserWeights:
         self.C = C
         self.layers = []
         ts = torch.as_tensor(timesteps, dtype=torch.long)
-        mods = []
         for i in range(num_layers):
             p = f"transformer_layers.{i}"
             L = {}
@@ -105,16 +104,12 @@ class DenoiserWeights:
             L["norm3.w"] = sd[f"{p}.norm3.weight"].detach().float().contiguous().to(device)
             L["norm3.b"] = sd[f"{p}.norm3.bias"].detach().float().contiguous().to(device)
             self.layers.append(L)
-            for n in ("norm1", "norm2"):
-                emb = sd[f"{p}.{n}.emb.weight"][ts].float().to(device)
-                a = torch.nn.functional.silu(emb).contiguous()
-                lin = Linear(sd[f"{p}.{n}.linear.weight"], sd[f"{p}.{n}.linear.bias"], device, False)
-                out = torch.empty(len(ts), 2 * C, device=device, dtype=torch.float32)
-                _lib.call("pfpp_gemm_f32", a.data_ptr(), C, lin.w32.data_ptr(), lin.k32, lin.b.data_ptr(), None, 0,
-                          out.data_ptr(), 2 * C, len(ts), 2 * C, C, EPI_NONE)
-                mods.append(out)
         # mod[(layer*2 + which)] : [T, 2C] -- rows selected per fragment by the current step index
-        self.mod = torch.stack(mods, 0).contiguous()
+        self._ada = [{k: sd[f"transformer_layers.{i}.{n}.{k}"].detach() for k in ("emb.weight", "linear.weight", "linear.bias")}
+                     for i in range(num_layers) for n in ("norm1", "norm2")]
+        self._device = device
+        self.mod = self.modulation_table(ts)
+        self._mod_all = None
         self.shape_embedding = Linear(sd["shape_embedding.weight"], sd["shape_embedding.bias"], device, bf16, split)
         self.param_fc = Linear(sd["param_fc.weight"], sd["param_fc.bias"], device, bf16, split)
         self.ref_emb = sd["ref_part_emb.weight"].detach().float().contiguous().to(device)
@@ -125,6 +120,30 @@ class DenoiserWeights:
         self.head_r2 = Linear(sd["mlp_out_rot.2.weight"], sd["mlp_out_rot.2.bias"], device, False)
         self.head_t4 = Linear(sd["mlp_out_trans.4.weight"], sd["mlp_out_trans.4.bias"], device, False)
         self.head_r4 = Linear(sd["mlp_out_rot.4.weight"], sd["mlp_out_rot.4.bias"], device, False)
+
+
+    def modulation_table(self, timesteps):
+        """MyAdaLayerNorm's Linear(SiLU(Embedding[t])) (attention.py:22-24) for the given timesteps ->
+        [2 * layers, len(timesteps), 2C] fp32 (row order: layer-major, norm1 then norm2)."""
+        ts = torch.as_tensor(timesteps, dtype=torch.long)
+        C, device = self.C, self._device
+        mods = []
+        for ada in self._ada:
+            emb = ada["emb.weight"][ts].float().to(device)
+            a = torch.nn.functional.silu(emb).contiguous()
+            lin = Linear(ada["linear.weight"], ada["linear.bias"], device, False)
+            out = torch.empty(len(ts), 2 * C, device=device, dtype=torch.float32)
+            _lib.call("pfpp_gemm_f32", a.data_ptr(), C, lin.w32.data_ptr(), lin.k32, lin.b.data_ptr(), None, 0,
+                      out.data_ptr(), 2 * C, len(ts), 2 * C, C, EPI_NONE)
+            mods.append(out)
+        return torch.stack(mods, 0).contiguous()
+
+    def mod_all(self, num_train_timesteps):
+        """the table for EVERY training timestep (row = t), built on first use: DenoiserTransformer.forward accepts
+        any timestep (training / validation forward, denoiser.py:80-113), not only the inference schedule's"""
+        if self._mod_all is None or self._mod_all.shape[1] != num_train_timesteps:
+            self._mod_all = self.modulation_table(range(num_train_timesteps))
+        return self._mod_all
 
 
 class VerifierWeights:

@@ -31,6 +31,34 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_binding_covers_header():
     from puzzlefusion_plusplus_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared()
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "pfpp.h")).read(), flags=re.S)
+    assert sorted(_lib.SIZE_FUNCS) == sorted(set(re.findall(r"\bsize_t\s+(pfpp_\w+)\s*\(", src)))
+
+
+def test_coarse_abi_struct_layouts_and_build_id():
+    """The ctypes mirrors of the weight structs have the layout the library was compiled with, and the loaded
+    binary was built from the sources of this tree (pfpp_build_id == hash of csrc/ + include/pfpp.h)."""
+    import ctypes as C
+    import importlib.util
+    import __graft_entry__
+    __graft_entry__.build()
+    from puzzlefusion_plusplus_b200 import _lib
+    lib = _lib.load()
+    for which, t in enumerate((_lib.PfppLinear, _lib.PfppEncoderWeights, _lib.PfppDenoiserLayer, _lib.PfppDenoiserWeights,
+                               _lib.PfppVerifierLayer, _lib.PfppVerifierWeights)):
+        assert lib.pfpp_struct_bytes(which) == C.sizeof(t), (which, t.__name__)
+    assert lib.pfpp_struct_bytes(99) == 0
+    for name in ("pfpp_encoder_forward", "pfpp_denoiser_step", "pfpp_denoiser_forward", "pfpp_verifier_forward",
+                 "pfpp_merge", "pfpp_edge_features", "pfpp_step_workspace_bytes"):
+        assert hasattr(lib, name), name  # the SURVEY 8(b) contract
+    spec = importlib.util.spec_from_file_location("pfpp_build", os.path.join(ROOT, "puzzlefusion-plusplus_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert lib.pfpp_build_id() == mod.source_id()
+    # argument errors of the coarse calls are negative codes before any CUDA work
+    null = C.c_void_p(None)
+    assert lib.pfpp_encoder_forward(null, null, null, null, 1, 8, null, null, null, null, 0, null) < 0
+    assert lib.pfpp_verifier_workspace_bytes(null, 10) == 0
 
 
 def test_sass_has_blackwell_tensor_and_tma_instructions():

@@ -180,7 +180,7 @@ def test_loop_config1_vs_reference_golden(engines):
 
 def test_loop_full_vs_oracle(engines, ckpt):
     """denoise + verify + merge (8 fragments, 4 steps, 4 outer iterations) vs the oracle loop with the
-    same noise: identical agglomeration decisions (pivots, reference promotion), poses within 2e-3."""
+    same noise: identical agglomeration decisions (pivots, reference promotion), poses and trajectory within 1e-4."""
     from puzzlefusion_plusplus_b200 import synthetic
     from puzzlefusion_plusplus_b200.loop import ReplayNoise, run_batch
     for seed in (321, 323):
@@ -197,14 +197,18 @@ def test_loop_full_vs_oracle(engines, ckpt):
         assert torch.equal(out["ref_part"][0], res["ref_part"])
         assert out["iters"][0] == res["iters"]
         valid = res["part_valids"] > 0
-        assert (out["x"][0][valid] - res["x"][valid]).abs().max() <= 2e-3
-        assert (out["pred_trans"][0, :8] - res["pred_trans"][:8]).abs().max() <= 2e-3
+        ex = (out["x"][0][valid] - res["x"][valid]).abs().max().item()
+        et = (out["pred_trans"][0, :8] - res["pred_trans"][:8]).abs().max().item()
+        etr = (out["trajectory"][0] - res["trajectory"][:, :8]).abs().max().item()
+        print(f"seed {seed}: |x| err {ex:.2e}, pred_trans err {et:.2e}, trajectory err {etr:.2e}")
+        assert ex <= 1e-4 and et <= 1e-4 and etr <= 1e-4, (ex, et, etr)
 
 
 def test_loop_full_batch_with_merges_vs_oracle(engines, ckpt):
     """B = 4 objects (8 / 12 / 10 / 9 fragments) through denoise -> verify -> batched device merge (pfpp_merge) for
     4 outer iterations of 4 DDPM steps, fp32 mode, against 4 single-object oracle runs on identical noise: identical
-    agglomeration decisions, merged-fragment poses and the recorded trajectory within the stated tolerance."""
+    agglomeration decisions (pivots, promotions, iteration counts); final poses, composed per-node poses and EVERY row
+    of the recorded trajectory within 1e-4 (the north star's tolerance)."""
     from puzzlefusion_plusplus_b200 import synthetic
     from puzzlefusion_plusplus_b200.loop import BatchRunner, run_interleaved
     T, iters = 4, 4
@@ -259,8 +263,33 @@ def test_loop_full_batch_with_merges_vs_oracle(engines, ckpt):
         # quaternion sign is fixed by matrix_to_quaternion's convention on both sides
         err_traj = (tr - tr_ref).abs().max().item()
         print(f"object {b}: |x| err {err_x:.2e}, pred_trans err {err_t:.2e}, trajectory err {err_traj:.2e}")
-        assert err_x <= 2e-3 and err_t <= 2e-3 and err_traj <= 2e-3, (b, err_x, err_t, err_traj)
+        # measured on a B200: 1e-7 .. 5e-5 (the object whose merged cloud is re-sampled twice); stated tolerance 1e-4
+        assert err_x <= 1e-4 and err_t <= 1e-4 and err_traj <= 1e-4, (b, err_x, err_t, err_traj)
     assert n_merged >= 2, "the test objects must exercise the merge stage"
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32", "tc32"])
+def test_coarse_c_abi_equals_kernel_sequence(engines, mode):
+    """The coarse C entry points (pfpp_denoiser_step = one call per DDPM step, pfpp_verifier_forward)
+    against the same kernels sequenced one by one from Python: bit-identical poses, trajectories and decisions over
+    two outer iterations with the verify / merge stage in between."""
+    from puzzlefusion_plusplus_b200 import synthetic
+    from puzzlefusion_plusplus_b200.loop import PerObjectNoise, run_batch
+    e = engines(mode, 4)
+    objs = [synthetic.make_object(700 + i, num_parts=n) for i, n in enumerate((6, 11, 4))]
+    outs = {}
+    try:
+        for coarse in (True, False):
+            e.coarse = coarse
+            outs[coarse] = run_batch(e, objs, max_iters=2, noise=PerObjectNoise(DEV, [21, 22, 23], 4), trajectory=True,
+                                     use_graph=coarse)
+    finally:
+        e.coarse = True
+    a, b = outs[True], outs[False]
+    assert torch.equal(a["x"], b["x"]) and torch.equal(a["pred_rots"], b["pred_rots"])
+    assert a["pivots"] == b["pivots"] and a["iters"] == b["iters"] and torch.equal(a["ref_part"], b["ref_part"])
+    for ta, tb in zip(a["trajectory"], b["trajectory"]):
+        assert torch.equal(ta, tb)
 
 
 def test_batch_equals_singles(engines):
