@@ -182,7 +182,7 @@ int pfpp_attention_tc_trace(const void* qkv, long long M, int ld, int C, const i
                             int n_segments, int max_len, int heads, int block, void* out, int ldo, long long* trace,
                             cudaStream_t stream);
 
-/* mean over L (denoiser_transformer.py:141-142). */
+/* mean over L (denoiser_transformer.py:141-142); out_bf16 == 2: split rows [F, 2C]. */
 int pfpp_mean_pool(const float* h, int F, int L, int C, int out_bf16, void* out, cudaStream_t stream);
 
 /* DDPMScheduler.step (diffusers 0.21.4; auto_aggl.py:149) + reference-part clamp (auto_aggl.py:150) +
@@ -297,7 +297,7 @@ typedef struct PfppDenoiserWeights {
   const float* mod;     /* [2 * n_layers, T, 2C]: AdaLN rows Linear(SiLU(Embedding[t])) for the T inference timesteps */
   const float* coef;    /* [T, 5] = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_x, sigma} (pfpp_ddpm_step) */
   PfppDenoiserLayer layers[PFPP_MAX_LAYERS];
-  PfppLinear head0, head_t2, head_r2, head_t4, head_r4; /* always fp32 */
+  PfppLinear head0, head_t2, head_r2, head_t4, head_r4; /* fp32 (mode 0) | split, as mode 2 (modes 1 and 2) */
 } PfppDenoiserWeights;
 
 typedef struct PfppVerifierLayer {
@@ -315,10 +315,11 @@ typedef struct PfppVerifierWeights {
 
 /* AutoAgglomerative._apply_rots + _extract_features (auto_aggl.py:70-92) for the F packed fragments frag_slot[f]:
  * part_pcs [slots,N,3], x [slots,7] pose rows (the quaternion is normalised here) -> z_q [F*L, latent_dim],
- * xyz [F,L,3], codes [F*L*latent_dim/16] (may be NULL). */
+ * xyz [F,L,3], codes [F*L*latent_dim/16] (may be NULL).  out_pos != NULL: fragment f's rows are written at row
+ * block out_pos[f] of z_q / xyz instead of f (a compacted pass filling its rows of a larger packed batch). */
 size_t pfpp_encoder_workspace_bytes(const PfppEncoderWeights* w, int F, int N);
 int pfpp_encoder_forward(const PfppEncoderWeights* w, const float* part_pcs, const int* frag_slot, const float* x, int F,
-                         int N, float* z_q, float* xyz, int* codes, void* workspace, size_t ws_bytes,
+                         int N, float* z_q, float* xyz, int* codes, const int* out_pos, void* workspace, size_t ws_bytes,
                          cudaStream_t stream);
 
 /* DenoiserTransformer.forward (denoiser_transformer.py:169-202) on the packed batch -> eps [F, 8] (columns 0..6).
@@ -333,14 +334,20 @@ int pfpp_denoiser_forward(const PfppDenoiserWeights* w, const float* x, const fl
 
 /* One whole DDPM step of auto_aggl.py:137-151 for the packed batch: step index = *step_counter (device) ->
  * encoder -> denoiser -> DDPMScheduler.step + reference clamp + history row -> *step_counter += 1.
- * noise [T, slots, 7] / x_hist [T, slots, 7] (row stride given; x_hist may be NULL); eps_out [F,8] may be NULL. */
+ * noise [T, slots, 7] / x_hist [T, slots, 7] (row stride given; x_hist may be NULL); eps_out [F,8] may be NULL.
+ * latent [F*L, latent_dim] / xyz [F,L,3] are caller-owned and persist from step to step: with enc_slot / enc_pos
+ * (F_enc entries: slot and packed position of the fragments to re-encode) only those fragments are encoded this
+ * step -- the reference parts, whose pose is clamped every step (auto_aggl.py:150), keep the rows the caller wrote
+ * once with pfpp_encoder_forward(out_pos) when the outer iteration began (same arithmetic, same results).
+ * enc_slot == NULL: every fragment of frag_slot is encoded. */
 size_t pfpp_step_workspace_bytes(const PfppEncoderWeights* we, const PfppDenoiserWeights* wd, int F, int N);
 int pfpp_denoiser_step(const PfppEncoderWeights* we, const PfppDenoiserWeights* wd, const float* part_pcs, float* x,
                        const float* scale, const unsigned char* ref, const float* ref_pose, const int* frag_slot,
                        int* frag_step, int* step_counter, const float* noise, long long noise_step_stride, float* x_hist,
                        long long hist_step_stride, const int* frag_seg_start, const int* frag_seg_len,
                        const int* obj_seg_start, const int* obj_seg_len, int F, int n_obj, int max_global, int N,
-                       float* eps_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+                       const int* enc_slot, const int* enc_pos, int F_enc, float* latent, float* xyz, float* eps_out,
+                       void* workspace, size_t ws_bytes, cudaStream_t stream);
 
 /* VerifierTransformer.forward (verifier_transformer.py:42-65) on packed valid-edge tokens (tok_row = dense edge row
  * b*E + e, tok_i / tok_j = fragment indices, one segment per object) -> logits [n_rows] (zero on invalid rows). */

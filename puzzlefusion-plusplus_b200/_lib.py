@@ -52,10 +52,10 @@ SIGNATURES = {
     "pfpp_verifier_head": [_P, _P, _I, _P, _P, _I, _P, _P],
     "pfpp_merge_filter": [_P, _I, _I, _I, _F, _P, _P, _P],
     "pfpp_nn_sqdist": [_P, _P, _I, _I, _I, _P, _P],
-    "pfpp_encoder_forward": [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, ctypes.c_size_t, _P],
+    "pfpp_encoder_forward": [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, ctypes.c_size_t, _P],
     "pfpp_denoiser_forward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, ctypes.c_size_t, _P],
     "pfpp_denoiser_step": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P,
-                           ctypes.c_size_t, _P],
+                           _I, _P, _P, _P, _P, ctypes.c_size_t, _P],
     "pfpp_verifier_forward": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _L, _P, _P, ctypes.c_size_t, _P],
     "pfpp_chamfer_forward": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "pfpp_chamfer_backward": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],

@@ -51,7 +51,7 @@ int gemm_f32(const float* a, int lda, const PfppLinear& lin, float* out, int ldc
 
 // ------------------------------------------------------------------------------------------------ encoder
 struct EncBufs {
-  float* z_e;
+  float *z_e, *zq_tmp, *xyz_tmp;
   float* rot;
   int* gidx;
   void *X, *B1, *B2, *B3;
@@ -83,6 +83,8 @@ EncBufs plan_encoder(Bump& b, const PfppEncoderWeights* w, int F, int N) {
   e.Fc = e.fused ? F : (w->chunk_frags < F ? w->chunk_frags : F);
   if (e.Fc < 1) e.Fc = 1;
   e.z_e = b.take<float>((size_t)F * L * w->latent_dim);
+  e.zq_tmp = b.take<float>((size_t)F * L * w->latent_dim);
+  e.xyz_tmp = b.take<float>((size_t)F * L * 3);
   e.rot = b.take<float>((size_t)e.Fc * N * 3);
   size_t max_rows = 0, mx = 0, m1 = 0, m2 = 0, m3 = 0;
   const int kmult = w->mode == 0 ? 4 : 8;
@@ -112,9 +114,24 @@ EncBufs plan_encoder(Bump& b, const PfppEncoderWeights* w, int F, int N) {
   return e;
 }
 
+// dst row pos[r] = src row r  (rows of `elems` floats): results of a compacted encoder pass into packed positions
+__global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ pos, int elems,
+                                    float* __restrict__ dst) {
+  const float* s = src + (size_t)blockIdx.x * elems;
+  float* d = dst + (size_t)pos[blockIdx.x] * elems;
+  for (int i = threadIdx.x; i < elems; i += blockDim.x) d[i] = s[i];
+}
+
+// out_pos != nullptr: fragment f's results go to rows out_pos[f] of z_q / xyz_out (encoded into scratch, then
+// scattered); nullptr: rows f.
 int run_encoder(const PfppEncoderWeights* w, const float* part_pcs, const int* frag_slot, const float* x, int F, int N,
-                float* z_q, float* xyz_out, int* codes, Bump& b, cudaStream_t s) {
+                float* z_q, float* xyz_out, int* codes, const int* out_pos, Bump& b, cudaStream_t s) {
   EncBufs e = plan_encoder(b, w, F, N);
+  float *z_dst = z_q, *xyz_dst = xyz_out;
+  if (out_pos) {
+    z_q = e.zq_tmp;
+    xyz_out = e.xyz_tmp;
+  }
   const int L = w->latent_points, mode = w->mode, wm = mode == 2 ? 2 : 1, kmult = mode == 0 ? 4 : 8;
   for (int c0 = 0; c0 < F; c0 += e.Fc) {
     const int K = e.Fc < F - c0 ? e.Fc : F - c0;
@@ -148,7 +165,12 @@ int run_encoder(const PfppEncoderWeights* w, const float* part_pcs, const int* f
     PF(gemm(mode, e.feats[2], w->conv6.k, w->conv6, e.z_e + (size_t)c0 * L * w->latent_dim, w->latent_dim, K * L, PFPP_EPI_NONE,
             nullptr, 0, false, s));
   }
-  return pfpp_vq(e.z_e, 0, (long long)F * L * (w->latent_dim / 16), w->codebook, w->n_codes, z_q, codes, s);
+  PF(pfpp_vq(e.z_e, 0, (long long)F * L * (w->latent_dim / 16), w->codebook, w->n_codes, z_q, codes, s));
+  if (out_pos) {
+    scatter_rows_kernel<<<F, 128, 0, s>>>(z_q, out_pos, L * w->latent_dim, z_dst);
+    scatter_rows_kernel<<<F, 96, 0, s>>>(xyz_out, out_pos, L * 3, xyz_dst);
+  }
+  PFPP_RETURN_LAST();
 }
 
 // ------------------------------------------------------------------------------------------------ denoiser
@@ -233,12 +255,28 @@ int run_denoiser(const PfppDenoiserWeights* w, const float* x, const float* scal
     PF(gemm(mode, d.ln, C, lw.ff1, d.ff, 4 * C, M, PFPP_EPI_GEGLU, nullptr, 0, true, s));
     PF(gemm(mode, d.ff, 4 * C, lw.ff2, d.h, C, M, PFPP_EPI_NONE, d.h, C, false, s));
   }
-  PF(pfpp_mean_pool(d.h, F, L, C, 0, d.pooled, s));
-  PF(gemm_f32(d.pooled, C, w->head0, d.h0, 2 * C, F, PFPP_EPI_SILU, s));
-  PF(gemm_f32(d.h0, 2 * C, w->head_t2, d.ht, C / 2, F, PFPP_EPI_SILU, s));
-  PF(gemm_f32(d.h0 + C, 2 * C, w->head_r2, d.hr, C / 2, F, PFPP_EPI_SILU, s));
-  PF(gemm_f32(d.ht, C / 2, w->head_t4, eps, 8, F, PFPP_EPI_NONE, s));
-  PF(gemm_f32(d.hr, C / 2, w->head_r4, eps + 3, 8, F, PFPP_EPI_NONE, s));
+  if (mode == 0) {
+    PF(pfpp_mean_pool(d.h, F, L, C, 0, d.pooled, s));
+    PF(gemm_f32(d.pooled, C, w->head0, d.h0, 2 * C, F, PFPP_EPI_SILU, s));
+    PF(gemm_f32(d.h0, 2 * C, w->head_t2, d.ht, C / 2, F, PFPP_EPI_SILU, s));
+    PF(gemm_f32(d.h0 + C, 2 * C, w->head_r2, d.hr, C / 2, F, PFPP_EPI_SILU, s));
+    PF(gemm_f32(d.ht, C / 2, w->head_t4, eps, 8, F, PFPP_EPI_NONE, s));
+    PF(gemm_f32(d.hr, C / 2, w->head_r4, eps + 3, 8, F, PFPP_EPI_NONE, s));
+    return PFPP_OK;
+  }
+  // tensor-core modes: the output heads (M = fragments: latency-bound as SIMT GEMMs) run as split-operand bf16x3
+  // GEMMs, fp32-grade; the same fp32 buffers hold the split rows (2 bf16 per fp32 slot)
+  __nv_bfloat16 *pooled = (__nv_bfloat16*)d.pooled, *h0 = (__nv_bfloat16*)d.h0, *ht = (__nv_bfloat16*)d.ht,
+                *hr = (__nv_bfloat16*)d.hr;
+  PF(pfpp_mean_pool(d.h, F, L, C, 2, pooled, s));
+  PF(gemm(2, pooled, C, w->head0, h0, 2 * C, F, PFPP_EPI_SILU, nullptr, 0, true, s));
+  // the trans / rot branches read the two halves of head0's output: hi at column offset 0 / C, lo 2C further
+  PF(pfpp_gemm_bf16x3(h0, 4 * C, w->head_t2.w, 2 * w->head_t2.k, w->head_t2.bias, nullptr, 0, ht, C, 1, F, w->head_t2.n,
+                      w->head_t2.k, PFPP_EPI_SILU, s));
+  PF(pfpp_gemm_bf16x3(h0 + C, 4 * C, w->head_r2.w, 2 * w->head_r2.k, w->head_r2.bias, nullptr, 0, hr, C, 1, F, w->head_r2.n,
+                      w->head_r2.k, PFPP_EPI_SILU, s));
+  PF(gemm(2, ht, C / 2, w->head_t4, eps, 8, F, PFPP_EPI_NONE, nullptr, 0, false, s));
+  PF(gemm(2, hr, C / 2, w->head_r4, eps + 3, 8, F, PFPP_EPI_NONE, nullptr, 0, false, s));
   return PFPP_OK;
 }
 
@@ -290,14 +328,14 @@ extern "C" size_t pfpp_encoder_workspace_bytes(const PfppEncoderWeights* w, int 
 }
 
 extern "C" int pfpp_encoder_forward(const PfppEncoderWeights* w, const float* part_pcs, const int* frag_slot, const float* x,
-                                    int F, int N, float* z_q, float* xyz, int* codes, void* workspace, size_t ws_bytes,
-                                    cudaStream_t stream) {
+                                    int F, int N, float* z_q, float* xyz, int* codes, const int* out_pos, void* workspace,
+                                    size_t ws_bytes, cudaStream_t stream) {
   PFPP_CHECK_ARG(w && part_pcs && frag_slot && x && z_q && xyz && workspace && F >= 0 && N > 0);
   PFPP_CHECK_ARG(w->mode >= 0 && w->mode <= 2 && w->latent_dim % 16 == 0);
   if (F == 0) return PFPP_OK;
   if (ws_bytes < pfpp_encoder_workspace_bytes(w, F, N)) return PFPP_EWORKSPACE;
   Bump b(workspace);
-  return run_encoder(w, part_pcs, frag_slot, x, F, N, z_q, xyz, codes, b, stream);
+  return run_encoder(w, part_pcs, frag_slot, x, F, N, z_q, xyz, codes, out_pos, b, stream);
 }
 
 extern "C" size_t pfpp_denoiser_workspace_bytes(const PfppDenoiserWeights* w, int F) {
@@ -326,9 +364,7 @@ extern "C" int pfpp_denoiser_forward(const PfppDenoiserWeights* w, const float* 
 extern "C" size_t pfpp_step_workspace_bytes(const PfppEncoderWeights* we, const PfppDenoiserWeights* wd, int F, int N) {
   if (!we || !wd || F < 0 || N <= 0) return 0;
   Bump b(nullptr);
-  b.take<float>((size_t)F * we->latent_points * we->latent_dim);  // latent
-  b.take<float>((size_t)F * we->latent_points * 3);               // xyz
-  b.take<float>((size_t)F * 8);                                   // eps
+  b.take<float>((size_t)F * 8);  // eps
   plan_encoder(b, we, F, N);
   plan_denoiser(b, wd, F);
   return b.off + 256;
@@ -339,22 +375,35 @@ extern "C" int pfpp_denoiser_step(const PfppEncoderWeights* we, const PfppDenois
                                   int* frag_step, int* step_counter, const float* noise, long long noise_step_stride,
                                   float* x_hist, long long hist_step_stride, const int* frag_seg_start,
                                   const int* frag_seg_len, const int* obj_seg_start, const int* obj_seg_len, int F, int n_obj,
-                                  int max_global, int N, float* eps_out, void* workspace, size_t ws_bytes,
-                                  cudaStream_t stream) {
+                                  int max_global, int N, const int* enc_slot, const int* enc_pos, int F_enc, float* latent,
+                                  float* xyz, float* eps_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   PFPP_CHECK_ARG(we && wd && part_pcs && x && scale && ref && ref_pose && frag_slot && frag_step && step_counter && noise &&
-                 frag_seg_start && frag_seg_len && obj_seg_start && obj_seg_len && workspace && F >= 0 && N > 0);
+                 frag_seg_start && frag_seg_len && obj_seg_start && obj_seg_len && latent && xyz && workspace && F >= 0 &&
+                 N > 0 && F_enc >= 0 && F_enc <= F && (F_enc == 0 || !enc_slot == !enc_pos));
   if (F == 0) return PFPP_OK;
   if (ws_bytes < pfpp_step_workspace_bytes(we, wd, F, N)) return PFPP_EWORKSPACE;
   Bump b(workspace);
-  float* latent = b.take<float>((size_t)F * we->latent_points * we->latent_dim);
-  float* xyz = b.take<float>((size_t)F * we->latent_points * 3);
   float* eps = b.take<float>((size_t)F * 8);
   if (eps_out) eps = eps_out;
   // frag_step[f] = *step_counter: selects the AdaLN row, the scheduler coefficients, the noise and history rows
   PF(pfpp_step_broadcast(step_counter, frag_step, F, stream));
-  PF(run_encoder(we, part_pcs, frag_slot, x, F, N, latent, xyz, nullptr, b, stream));
+  if (enc_slot) {
+    // only the fragments whose pose changes from step to step are re-encoded; the rows of the others (reference
+    // parts: their pose is clamped every step, auto_aggl.py:150) were written once when the iteration began
+    if (F_enc > 0) PF(run_encoder(we, part_pcs, enc_slot, x, F_enc, N, latent, xyz, nullptr, enc_pos, b, stream));
+  } else {
+    PF(run_encoder(we, part_pcs, frag_slot, x, F, N, latent, xyz, nullptr, nullptr, b, stream));
+  }
+  Bump b2(workspace);
+  b2.off = (size_t)F * 8 * sizeof(float);
+  {  // the denoiser's buffers follow the (F-sized) encoder plan, whatever F_enc is
+    Bump skip(nullptr);
+    skip.off = b2.off;
+    plan_encoder(skip, we, F, N);
+    b2.off = skip.off;
+  }
   PF(run_denoiser(wd, x, scale, ref, frag_slot, frag_step, latent, xyz, frag_seg_start, frag_seg_len, obj_seg_start,
-                  obj_seg_len, F, n_obj, max_global, eps, b, stream));
+                  obj_seg_len, F, n_obj, max_global, eps, b2, stream));
   PF(pfpp_ddpm_step(eps, 8, frag_slot, wd->coef, frag_step, 1, noise, noise_step_stride, ref, ref_pose, F, x, x_hist,
                     hist_step_stride, stream));
   return pfpp_step_advance(step_counter, stream);

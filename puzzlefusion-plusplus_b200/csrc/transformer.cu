@@ -356,21 +356,22 @@ extern "C" int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_o
 }
 
 // mean over the L tokens of each fragment (denoiser_transformer.py:141-142): [F*L, C] -> [F, C]
-template <typename OutT>
+template <typename OutT, bool SPLIT>
 __global__ void mean_pool_kernel(const float* __restrict__ h, int L, int C, OutT* __restrict__ out) {
   int f = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (int l = 0; l < L; ++l) s += h[((size_t)f * L + l) * C + c];
-    out[(size_t)f * C + c] = cvt_out<OutT>(s / (float)L);
+    put_out<OutT, SPLIT>(out + (size_t)f * (SPLIT ? 2 * C : C) + c, C, s / (float)L);
   }
 }
 
 extern "C" int pfpp_mean_pool(const float* h, int F, int L, int C, int out_bf16, void* out, cudaStream_t stream) {
   PFPP_CHECK_ARG(h && out);
   if (F == 0) return PFPP_OK;
-  if (out_bf16) mean_pool_kernel<__nv_bfloat16><<<F, 128, 0, stream>>>(h, L, C, (__nv_bfloat16*)out);
-  else mean_pool_kernel<float><<<F, 128, 0, stream>>>(h, L, C, (float*)out);
+  if (out_bf16 == 2) mean_pool_kernel<__nv_bfloat16, true><<<F, 128, 0, stream>>>(h, L, C, (__nv_bfloat16*)out);  // [F, 2C] split
+  else if (out_bf16) mean_pool_kernel<__nv_bfloat16, false><<<F, 128, 0, stream>>>(h, L, C, (__nv_bfloat16*)out);
+  else mean_pool_kernel<float, false><<<F, 128, 0, stream>>>(h, L, C, (float*)out);
   PFPP_RETURN_LAST();
 }
 

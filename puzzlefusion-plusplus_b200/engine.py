@@ -79,6 +79,9 @@ class Engine:
         self.fused_sa = True     # fused gather + 3-layer MLP + max tcgen05 kernel in bf16 mode
         self.local_tiles = 4     # 125-token tiles (5 fragments) per local-attention CTA, two per softmax group
         self.coarse = True       # run the stages through the coarse C entry points (pfpp_encoder_forward, ...)
+        # Reference parts keep their pose for a whole outer iteration (clamped every step, auto_aggl.py:150), so their
+        # encoder output is the same at every DDPM step: encode them once per iteration, re-encode only the others.
+        self.cache_ref = True
         self._ws = {}
         self._ws_version = 0
         self._build_weight_structs()
@@ -132,7 +135,7 @@ class Engine:
             L.ff1, L.ff2 = self._lin(lw["ff1"], m), self._lin(lw["ff2"], m)
             L.norm3_w, L.norm3_b = lw["norm3.w"].data_ptr(), lw["norm3.b"].data_ptr()
         for name in ("head0", "head_t2", "head_r2", "head_t4", "head_r4"):
-            setattr(wd, name, self._lin(getattr(w, name), 0))
+            setattr(wd, name, self._lin(getattr(w, name), 0 if m == 0 else 2))
         self.cw_den = wd
         self.cw_ver = None
         if self.ver is not None:
@@ -281,7 +284,7 @@ class Engine:
             n = int(_lib.load().pfpp_encoder_workspace_bytes(ctypes.byref(self.cw_enc), F, N))
             ws = self.buf("enc_ws", (n,), torch.uint8)
             call("pfpp_encoder_forward", ctypes.byref(self.cw_enc), part_pcs.data_ptr(), frag_slot.data_ptr(), x.data_ptr(), F,
-                 N, latent.data_ptr(), xyz_out.data_ptr(), None, ws.data_ptr(), n)
+                 N, latent.data_ptr(), xyz_out.data_ptr(), None, None, ws.data_ptr(), n)
             return latent, xyz_out
         z_e = self.buf("z_e", (F * L, self.latent_dim), torch.float32)
         xyz_out = self.buf("xyz3", (F, L, 3), torch.float32)
@@ -445,23 +448,51 @@ class Engine:
             if trace is not None:
                 trace[f"layer{li}"] = h.clone()
         eps = self.buf("eps", (F, 8), torch.float32)
-        pooled = self.buf("pooled", (F, C), torch.float32)
-        h0 = self.buf("head0", (F, 2 * C), torch.float32)
-        ht = self.buf("head_t", (F, C // 2), torch.float32)
-        hr = self.buf("head_r", (F, C // 2), torch.float32)
-        call("pfpp_mean_pool", h.data_ptr(), F, L, C, 0, pooled.data_ptr())
-        self.gemm(pooled, C, w.head0, h0, 2 * C, F, EPI_SILU, force_f32=True)
-        self.gemm(h0, 2 * C, w.head_t2, ht, C // 2, F, EPI_SILU, force_f32=True)
-        self.gemm(h0[:, C:], 2 * C, w.head_r2, hr, C // 2, F, EPI_SILU, force_f32=True)
-        self.gemm(ht, C // 2, w.head_t4, eps, 8, F, EPI_NONE, force_f32=True)
-        self.gemm(hr, C // 2, w.head_r4, eps[:, 3:], 8, F, EPI_NONE, force_f32=True)
+        if self.mode == 0:
+            pooled = self.buf("pooled", (F, C), torch.float32)
+            h0 = self.buf("head0", (F, 2 * C), torch.float32)
+            ht = self.buf("head_t", (F, C // 2), torch.float32)
+            hr = self.buf("head_r", (F, C // 2), torch.float32)
+            call("pfpp_mean_pool", h.data_ptr(), F, L, C, 0, pooled.data_ptr())
+            self.gemm(pooled, C, w.head0, h0, 2 * C, F, EPI_SILU, force_f32=True)
+            self.gemm(h0, 2 * C, w.head_t2, ht, C // 2, F, EPI_SILU, force_f32=True)
+            self.gemm(h0[:, C:], 2 * C, w.head_r2, hr, C // 2, F, EPI_SILU, force_f32=True)
+            self.gemm(ht, C // 2, w.head_t4, eps, 8, F, EPI_NONE, force_f32=True)
+            self.gemm(hr, C // 2, w.head_r4, eps[:, 3:], 8, F, EPI_NONE, force_f32=True)
+            return eps
+        # tensor-core modes: split-operand bf16x3 GEMMs (fp32-grade) instead of latency-bound SIMT GEMMs with M = F
+        bf = torch.bfloat16
+        pooled = self.buf("pooled_s", (F, 2 * C), bf)
+        h0 = self.buf("head0_s", (F, 4 * C), bf)      # [hi: trans | rot , lo: trans | rot]
+        ht = self.buf("head_t_s", (F, C), bf)
+        hr = self.buf("head_r_s", (F, C), bf)
+        call("pfpp_mean_pool", h.data_ptr(), F, L, C, 2, pooled.data_ptr())
+        self.gemm(pooled, C, w.head0, h0, 2 * C, F, EPI_SILU, split=True)
+        for lin, off, dst in ((w.head_t2, 0, ht), (w.head_r2, C, hr)):
+            call("pfpp_gemm_bf16x3", h0.data_ptr() + 2 * off, 4 * C, lin.w16s.data_ptr(), 2 * lin.k16, lin.b.data_ptr(), None, 0,
+                 dst.data_ptr(), C, 1, F, lin.n, lin.k16, EPI_SILU)
+        self.gemm(ht, C // 2, w.head_t4, eps, 8, F, EPI_NONE, split=True)
+        self.gemm(hr, C // 2, w.head_r4, eps[:, 3:], 8, F, EPI_NONE, split=True)
         return eps
 
     # ------------------------------------------------------------------ one whole DDPM step (coarse C ABI)
+    def encode_into(self, part_pcs, slots, pos, x, N, latent, xyz):
+        """Encode the fragments `slots` (device int32) and write their rows at packed positions `pos` of latent
+        [F*L, latent_dim] / xyz [F, L, 3]: the once-per-outer-iteration pass over the reference parts."""
+        Fe = slots.numel()
+        if Fe == 0:
+            return
+        self._sync_switches()
+        n = int(_lib.load().pfpp_encoder_workspace_bytes(ctypes.byref(self.cw_enc), Fe, N))
+        ws = self.buf("enc_ws", (n,), torch.uint8)
+        call("pfpp_encoder_forward", ctypes.byref(self.cw_enc), part_pcs.data_ptr(), slots.data_ptr(), x.data_ptr(), Fe, N,
+             latent.data_ptr(), xyz.data_ptr(), None, pos.data_ptr(), ws.data_ptr(), n)
+
     def ddpm_step(self, part_pcs, x, scale, ref, ref_pose, frag_slot, frag_step, step_ctr, noise_all, hist, seg_local,
-                  seg_global, max_global, N):
+                  seg_global, max_global, N, latent, xyz, enc_slot=None, enc_pos=None, n_enc=0):
         """auto_aggl.py:137-151 for the packed batch in ONE C call (pfpp_denoiser_step): step-counter broadcast,
-        encoder, denoiser, scheduler step + reference clamp + history row, counter advance."""
+        encoder (all fragments, or only enc_slot -> rows enc_pos when the reference parts' rows are cached),
+        denoiser, scheduler step + reference clamp + history row, counter advance."""
         self._sync_switches()
         F = frag_slot.numel()
         n = int(_lib.load().pfpp_step_workspace_bytes(ctypes.byref(self.cw_enc), ctypes.byref(self.cw_den), F, N))
@@ -470,7 +501,8 @@ class Engine:
              scale.data_ptr(), ref.data_ptr(), ref_pose.data_ptr(), frag_slot.data_ptr(), frag_step.data_ptr(),
              step_ctr.data_ptr(), noise_all.data_ptr(), noise_all.stride(0), hist.data_ptr(), hist.stride(0),
              seg_local[0].data_ptr(), seg_local[1].data_ptr(), seg_global[0].data_ptr(), seg_global[1].data_ptr(), F,
-             seg_global[0].numel(), max_global, N, None, ws.data_ptr(), n, kernels=self.step_kernels(F))
+             seg_global[0].numel(), max_global, N, _lib.ptr(enc_slot), _lib.ptr(enc_pos), n_enc, latent.data_ptr(),
+             xyz.data_ptr(), None, ws.data_ptr(), n, kernels=self.step_kernels(F))
 
     # ------------------------------------------------------------------ verifier
     def verifier_logits(self, feat, tok_row, tok_i, tok_j, seg_start, seg_len, max_len, n_rows):

@@ -215,15 +215,18 @@ class StepContext:
         self.step_ctr = torch.zeros(1, **i32)
         self.part_pcs = torch.empty(slots, N, 3, **f32)
         self.scale = torch.empty(slots, **f32)
+        self.latent = torch.empty(F * e.L, e.latent_dim, **f32)  # encoder outputs, persistent across the steps
+        self.xyz = torch.empty(F, e.L, 3, **f32)
+        self.enc = torch.empty(2, F, **i32)                      # [slot | packed position] of the re-encoded fragments
         self.graph = None
         self.ws_version = -1
         self.owner = None  # the live BatchRunner whose poses / noise / clouds these buffers currently hold
 
     @staticmethod
-    def get(e, slots, N, F, n_obj, max_global):
+    def get(e, slots, N, F, n_obj, max_global, n_enc=-1):
         # the launch sequence also depends on the engine's kernel-selection switches: part of the key, so that a
         # graph captured under other settings is never replayed
-        key = (slots, N, F, n_obj, max_global, e.T, e.fused_sa, e.tc_attention, e.local_tiles, e.coarse)
+        key = (slots, N, F, n_obj, max_global, e.T, e.fused_sa, e.tc_attention, e.local_tiles, e.coarse, n_enc)
         cache = e._step_ctx
         ctx = cache.pop(key, None)
         if ctx is None:
@@ -303,12 +306,18 @@ class BatchRunner:
             counts.append(len(s))
         self.F = len(slots)
         self.frag_iterations += self.F  # workload statistic: valid fragments x outer iterations they take part in
-        frag_slot = torch.as_tensor(np.asarray(slots, dtype=np.int32))
+        slots_np = np.asarray(slots, dtype=np.int32)
+        frag_slot = torch.as_tensor(slots_np)
         noise_all = self.noise.iteration_noise(st.B, P, self.timesteps, self.active)
+        # reference parts are encoded once per iteration, the rest every step (engine.cache_ref)
+        cache = e.coarse and getattr(e, "cache_ref", False) and self.record is None
+        is_ref = st.ref.reshape(-1)[slots_np]
+        pos_ref, pos_enc = np.nonzero(is_ref)[0].astype(np.int32), np.nonzero(~is_ref)[0].astype(np.int32)
+        self.n_enc = len(pos_enc) if cache else -1
         if self.use_graph:
             # persistent buffers + cached graph of this batch geometry: copy this iteration's inputs in
             max_global = int(max(counts)) * e.L
-            ctx = self.ctx = StepContext.get(e, st.B * P, st.N, self.F, len(counts), max_global)
+            ctx = self.ctx = StepContext.get(e, st.B * P, st.N, self.F, len(counts), max_global, self.n_enc)
             if ctx.owner is not None and ctx.owner is not self and not ctx.owner.finished:
                 raise _lib.PfppError("two live BatchRunners of the same batch geometry share one Engine: its step "
                                      "buffers and CUDA graph cannot serve both (one Engine per concurrent batch)")
@@ -331,6 +340,7 @@ class BatchRunner:
             self.frag_slot, self.frag_step, self.noise_all, self.step_ctr = ctx.frag_slot, ctx.frag_step, ctx.noise_all, ctx.step_ctr
             self.seg_local, self.seg_global, self.max_global = ctx.loc, ctx.glo, max_global
             self.pcs, self.scale_dev, self.hist = ctx.part_pcs, ctx.scale, ctx.x_hist
+            self.latent, self.xyz, enc_buf = ctx.latent, ctx.xyz, ctx.enc
             self.graph = ctx.graph if ctx.ws_version == e._ws_version else None
             self.graph_launches = getattr(ctx, "graph_launches", 0)
         else:
@@ -341,7 +351,18 @@ class BatchRunner:
             self.noise_all = noise_all
             self.step_ctr.zero_()
             self.pcs, self.scale_dev, self.hist = st.part_pcs, st.scale, self.x_hist[self.it * e.T:]
+            self.latent = torch.empty(self.F * e.L, e.latent_dim, device=e.device)
+            self.xyz = torch.empty(self.F, e.L, 3, device=e.device)
+            enc_buf = torch.empty(2, self.F, dtype=torch.int32, device=e.device)
             self.graph = None
+        self.enc_slot = self.enc_pos = None
+        if cache:
+            # [slot | packed position] of the fragments re-encoded every step, and of the reference parts encoded now
+            tab = np.stack([np.concatenate([slots_np[pos_enc], slots_np[pos_ref]]), np.concatenate([pos_enc, pos_ref])])
+            enc_buf.copy_(e.upload_array("enc_tab", tab.astype(np.int32)), non_blocking=True)
+            self.enc_slot, self.enc_pos = enc_buf[0], enc_buf[1]
+            ne = self.n_enc
+            e.encode_into(self.pcs, enc_buf[0, ne:], enc_buf[1, ne:], self.x, st.N, self.latent, self.xyz)
         self.si = 0
         return True
 
@@ -350,7 +371,8 @@ class BatchRunner:
         if e.coarse and self.record is None:
             # the whole step is one C call (pfpp_denoiser_step)
             e.ddpm_step(self.pcs, self.x, self.scale_dev, self.ref_dev, self.ref_pose, self.frag_slot, self.frag_step,
-                        self.step_ctr, self.noise_all, self.hist, self.seg_local, self.seg_global, self.max_global, st.N)
+                        self.step_ctr, self.noise_all, self.hist, self.seg_local, self.seg_global, self.max_global, st.N,
+                        self.latent, self.xyz, self.enc_slot, self.enc_pos, max(self.n_enc, 0))
             return None
         call("pfpp_step_broadcast", self.step_ctr.data_ptr(), self.frag_step.data_ptr(), self.F)
         latent, xyz = e.encode(self.pcs, self.frag_slot, self.x, st.N)

@@ -114,12 +114,14 @@ class DenoiserWeights:
         self.param_fc = Linear(sd["param_fc.weight"], sd["param_fc.bias"], device, bf16, split)
         self.ref_emb = sd["ref_part_emb.weight"].detach().float().contiguous().to(device)
         self.pe = sd["pos_encoding.pe"][0].detach().float().contiguous().to(device)  # [P, C]
+        # output heads: fp32 SIMT in fp32 mode, split-operand (fp32-grade) tensor-core GEMMs in the other modes
+        hs = bf16 or split
         self.head0 = Linear(torch.cat([sd["mlp_out_trans.0.weight"], sd["mlp_out_rot.0.weight"]], 0),
-                            torch.cat([sd["mlp_out_trans.0.bias"], sd["mlp_out_rot.0.bias"]], 0), device, False)
-        self.head_t2 = Linear(sd["mlp_out_trans.2.weight"], sd["mlp_out_trans.2.bias"], device, False)
-        self.head_r2 = Linear(sd["mlp_out_rot.2.weight"], sd["mlp_out_rot.2.bias"], device, False)
-        self.head_t4 = Linear(sd["mlp_out_trans.4.weight"], sd["mlp_out_trans.4.bias"], device, False)
-        self.head_r4 = Linear(sd["mlp_out_rot.4.weight"], sd["mlp_out_rot.4.bias"], device, False)
+                            torch.cat([sd["mlp_out_trans.0.bias"], sd["mlp_out_rot.0.bias"]], 0), device, False, hs)
+        self.head_t2 = Linear(sd["mlp_out_trans.2.weight"], sd["mlp_out_trans.2.bias"], device, False, hs)
+        self.head_r2 = Linear(sd["mlp_out_rot.2.weight"], sd["mlp_out_rot.2.bias"], device, False, hs)
+        self.head_t4 = Linear(sd["mlp_out_trans.4.weight"], sd["mlp_out_trans.4.bias"], device, False, hs)
+        self.head_r4 = Linear(sd["mlp_out_rot.4.weight"], sd["mlp_out_rot.4.bias"], device, False, hs)
 
 
     def modulation_table(self, timesteps):

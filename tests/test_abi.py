@@ -57,7 +57,7 @@ def test_coarse_abi_struct_layouts_and_build_id():
     assert lib.pfpp_build_id() == mod.source_id()
     # argument errors of the coarse calls are negative codes before any CUDA work
     null = C.c_void_p(None)
-    assert lib.pfpp_encoder_forward(null, null, null, null, 1, 8, null, null, null, null, 0, null) < 0
+    assert lib.pfpp_encoder_forward(null, null, null, null, 1, 8, null, null, null, null, null, 0, null) < 0
     assert lib.pfpp_verifier_workspace_bytes(null, 10) == 0
 
 

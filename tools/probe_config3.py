@@ -50,7 +50,7 @@ def main():
             r.end_iteration()
             torch.cuda.synchronize()
             t3 = time.perf_counter()
-            print(f"rep {rep} iter {it}: active {len(r.active)} F {r.F} | ddpm {1e3 * (t2 - t1):.1f} ms "
+            print(f"rep {rep} iter {it}: active {len(r.active)} F {r.F} (re-encoded per step: {r.n_enc}) | ddpm {1e3 * (t2 - t1):.1f} ms "
                   f"({1e3 * (t2 - t1) / eng.T:.2f}/step) | verify+merge {1e3 * (t3 - t2):.1f} ms | valid fragments "
                   f"{int(valid_before)} -> {int(r.st.valid.sum())} | done {sum(r.st.done)}")
             it += 1
