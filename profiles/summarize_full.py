@@ -37,14 +37,15 @@ def main(path, peak=6538.3):
     ki = h.index("Kernel Name")
     idx = {k: (h.index(v) if v in h else None) for k, v in COLS.items()}
     agg = collections.OrderedDict()
+    gi = h.index("Grid Size") if "Grid Size" in h else None
     for r in rows[hdr + 2:]:
         if len(r) <= ki:
             continue
-        m = re.search(r"(\w+_kernel)", r[ki])
-        name = m.group(1) if m else r[ki][:48]
-        tm = re.search(r"<(.*)>", r[ki])
-        if m and tm and name in ("sa_fused_kernel", "sa_resident_kernel", "fps_kernel", "gemm_bf16_tc3_kernel", "gemm_bf16_tc_kernel"):
-            name += "<" + tm.group(1)[:28] + ">"
+        full = r[ki].replace("<unnamed>::", "").replace("void ", "")
+        m = re.match(r"([\w:]+?_kernel)(<[^(]*>)?\(", full)
+        name = (m.group(1) + (m.group(2) or "")) if m else full[:48]
+        if name.startswith(("gemm_bf16_tc", "gemm_f32", "attention_ws", "attn_varlen", "fps_kernel", "layernorm")) and gi is not None:
+            name += " grid " + r[gi].replace(" ", "")  # one row per launch shape
         vals = {}
         for k, i in idx.items():
             if i is None:
@@ -58,7 +59,7 @@ def main(path, peak=6538.3):
         for k, v in vals.items():
             a[k].append(v)
     mean = lambda xs: sum(xs) / len(xs) if xs else float("nan")  # noqa: E731
-    print(f"{'kernel':58s} {'n':>4s} {'us':>8s} {'DRAM MB':>8s} {'GB/s':>7s} {'%HBM':>5s} {'tensor%':>7s} {'warps%':>6s} {'issue%':>6s} {'regs':>4s} {'smemKB':>6s} {'grid':>6s}")
+    print(f"{'kernel (one row per template instantiation / launch shape)':58s} {'n':>4s} {'us':>8s} {'DRAM MB':>8s} {'GB/s':>7s} {'%HBM':>5s} {'tensor%':>7s} {'warps%':>6s} {'issue%':>6s} {'regs':>4s} {'smemKB':>6s} {'grid':>6s}")
     for name, a in sorted(agg.items(), key=lambda kv: -sum(kv[1]["dur"])):
         dur = mean(a["dur"])
         traffic = mean(a["rd"]) + mean(a["wr"])

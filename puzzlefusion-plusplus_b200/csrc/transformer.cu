@@ -125,16 +125,27 @@ extern "C" int pfpp_embed_features(const float* x, const float* scale, const int
 __global__ void combine_embed_kernel(const float* __restrict__ shape_emb, const float* __restrict__ x_emb,
                                      const float* __restrict__ ref_emb, const float* __restrict__ pe,
                                      const int* __restrict__ frag_slot, const unsigned char* __restrict__ ref, int P,
-                                     int L, int C, float* __restrict__ h) {
-  int row = blockIdx.x;
-  int f = row / L;
-  int slot = frag_slot[f];
-  const float* re = ref_emb + (size_t)(ref[slot] ? 1 : 0) * C;
-  const float* pp = pe + (size_t)(slot % P) * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float xe = fadd(x_emb[(size_t)f * C + c], re[c]);
-    float d = fadd(xe, shape_emb[(size_t)row * C + c]);
-    h[(size_t)row * C + c] = fadd(d, pp[c]);
+                                     int L, int C, long long rows, float* __restrict__ h) {
+  // one warp per token row, float4 per lane, grid-stride
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+       row += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int f = (int)(row / L);
+    const int slot = frag_slot[f];
+    const float* re = ref_emb + (size_t)(ref[slot] ? 1 : 0) * C;
+    const float* pp = pe + (size_t)(slot % P) * C;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 xe = *reinterpret_cast<const float4*>(x_emb + (size_t)f * C + c);
+      const float4 r4 = *reinterpret_cast<const float4*>(re + c);
+      const float4 se = *reinterpret_cast<const float4*>(shape_emb + (size_t)row * C + c);
+      const float4 p4 = *reinterpret_cast<const float4*>(pp + c);
+      float4 o;
+      o.x = fadd(fadd(fadd(xe.x, r4.x), se.x), p4.x);
+      o.y = fadd(fadd(fadd(xe.y, r4.y), se.y), p4.y);
+      o.z = fadd(fadd(fadd(xe.z, r4.z), se.z), p4.z);
+      o.w = fadd(fadd(fadd(xe.w, r4.w), se.w), p4.w);
+      *reinterpret_cast<float4*>(h + (size_t)row * C + c) = o;
+    }
   }
 }
 
@@ -142,8 +153,12 @@ extern "C" int pfpp_combine_embed(const float* shape_emb, const float* x_emb, co
                                   const int* frag_slot, const unsigned char* ref, int F, int P, int L, int C, float* h,
                                   cudaStream_t stream) {
   PFPP_CHECK_ARG(shape_emb && x_emb && ref_emb && pe && frag_slot && ref && h);
+  PFPP_CHECK_ARG((C % 4) == 0);
   if (F == 0) return PFPP_OK;
-  combine_embed_kernel<<<F * L, 128, 0, stream>>>(shape_emb, x_emb, ref_emb, pe, frag_slot, ref, P, L, C, h);
+  const long long rows = (long long)F * L;
+  int grid = pfpp_cdiv(rows, 8);
+  if (grid > 148 * 8) grid = 148 * 8;
+  combine_embed_kernel<<<grid, 256, 0, stream>>>(shape_emb, x_emb, ref_emb, pe, frag_slot, ref, P, L, C, rows, h);
   PFPP_RETURN_LAST();
 }
 
@@ -158,10 +173,11 @@ __global__ void __launch_bounds__(256)
     layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ mod, const int* __restrict__ row_group,
                      int rows_per_group, long long rows, OutT* __restrict__ y, float* __restrict__ sum_out) {
-  long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   constexpr int PER = C / 32;
+  // grid-stride over rows: the grid is capped at one resident wave (a tail wave of a few blocks would cost a whole
+  // extra wave of latency on a kernel that lasts ~10 us)
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
   float v[PER];
   float s = 0.f;
 #pragma unroll
@@ -218,6 +234,7 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<float4*>(yo) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
+  }  // row loop
 }
 
 extern "C" int pfpp_layernorm(const float* x, const float* residual, const float* gamma, const float* beta,
@@ -227,6 +244,7 @@ extern "C" int pfpp_layernorm(const float* x, const float* residual, const float
   PFPP_CHECK_ARG(!mod || (row_group && rows_per_group > 0));
   if (rows == 0) return PFPP_OK;
   int grid = pfpp_cdiv(rows, 8);
+  if (grid > 148 * 8) grid = 148 * 8;  // one resident wave (256 threads, <= 48 registers: 8 blocks per SM)
 #define PFPP_LN_CASE(CC, T, SP)                                                                                   \
   layernorm_kernel<CC, T, SP><<<grid, 256, 0, stream>>>(x, residual, gamma, beta, mod, row_group, rows_per_group, \
                                                         rows, (T*)y, sum_out)
@@ -251,37 +269,47 @@ extern "C" int pfpp_layernorm(const float* x, const float* residual, const float
 //   attention over the valid fragments of an object (<=500 tokens, padded fragments are simply
 //   not in the packed batch, which is what the reference's key mask achieves), and the verifier's
 //   key-padded attention over valid edges.
-//   One thread per query row (q and the output accumulator in registers), K/V tiles of 32 keys
-//   staged in shared memory and read as broadcast LDS.128.
+//   Four lanes per query row (q and the output accumulator in registers, a quarter each), K/V tiles of 32 keys
+//   staged in shared memory.
 // ---------------------------------------------------------------------------------------------
 #define ATT_KT 32
-
+#define ATT_QPB 32  // queries per block (4 lanes each)
+// Four lanes share one query row: lane `sub` owns the 16-byte chunks c = 4 i + sub of the head dimension (so the four
+// lanes of a query read 64 contiguous bytes of a K / V row: one conflict-free wavefront), i.e. D/4 of the q values
+// and of the output accumulator.  A score is the sum of the four partial dot products (two xor-shuffles).  Compared
+// with one thread per query this quarters the registers per thread (q + acc = D/2 instead of 2 D), which is what
+// bounds the occupancy -- and with it the latency hiding -- of this kernel.
 template <int D, typename InT, typename OutT, bool SPLIT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(4 * ATT_QPB)
     attn_varlen_kernel(const InT* __restrict__ qkv, int ld, int q_off, int k_off, int v_off,
                        const int* __restrict__ seg_start, const int* __restrict__ seg_len, float scale,
                        OutT* __restrict__ out, int ldo) {
+  constexpr int NC = D / 16;  // 16-byte chunks per lane
   __shared__ __align__(16) float Ks[ATT_KT][D];
   __shared__ __align__(16) float Vs[ATT_KT][D];
   const int s = blockIdx.z, h = blockIdx.y;
   const int len = seg_len[s], st = seg_start[s];
-  const int q0 = blockIdx.x * blockDim.x;
+  const int q0 = blockIdx.x * ATT_QPB;
   if (q0 >= len) return;
-  const int qi = q0 + threadIdx.x;
+  const int sub = threadIdx.x & 3;
+  const int qi = q0 + (threadIdx.x >> 2);
   const bool active = qi < len;
-  float q[D], acc[D];
+  float q[NC * 4], acc[NC * 4];
 #pragma unroll
-  for (int d = 0; d < D; ++d) {
-    q[d] = active ? (float)qkv[(size_t)(st + qi) * ld + q_off + h * D + d] * scale : 0.f;
-    acc[d] = 0.f;
-  }
+  for (int i = 0; i < NC; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = (4 * i + sub) * 4 + e;
+      q[4 * i + e] = active ? (float)qkv[(size_t)(st + qi) * ld + q_off + h * D + d] * scale : 0.f;
+      acc[4 * i + e] = 0.f;
+    }
   float m = -INFINITY, l = 0.f;
   for (int kt = 0; kt < len; kt += ATT_KT) {
-    int nk = min(ATT_KT, len - kt);
+    const int nk = min(ATT_KT, len - kt);
     __syncthreads();
     for (int i = threadIdx.x; i < nk * D; i += blockDim.x) {
-      int r = i / D, d = i - r * D;
-      size_t base = (size_t)(st + kt + r) * ld + h * D + d;
+      const int r = i / D, d = i - r * D;
+      const size_t base = (size_t)(st + kt + r) * ld + h * D + d;
       Ks[r][d] = (float)qkv[base + k_off];
       Vs[r][d] = (float)qkv[base + v_off];
     }
@@ -290,43 +318,46 @@ __global__ void __launch_bounds__(128)
     float tmax = -INFINITY;
 #pragma unroll
     for (int j = 0; j < ATT_KT; ++j) {
-      float a = 0.f;
-      if (j < nk) {
+      float a = -INFINITY;
+      if (j < nk) {  // block-uniform
+        a = 0.f;
 #pragma unroll
-        for (int d = 0; d < D; d += 4) {
-          float4 kv = *reinterpret_cast<const float4*>(&Ks[j][d]);
-          a += q[d] * kv.x + q[d + 1] * kv.y + q[d + 2] * kv.z + q[d + 3] * kv.w;
+        for (int i = 0; i < NC; ++i) {
+          const float4 kv = *reinterpret_cast<const float4*>(&Ks[j][(4 * i + sub) * 4]);
+          a += q[4 * i] * kv.x + q[4 * i + 1] * kv.y + q[4 * i + 2] * kv.z + q[4 * i + 3] * kv.w;
         }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
         tmax = fmaxf(tmax, a);
-      } else {
-        a = -INFINITY;
       }
       sc[j] = a;
     }
-    float mn = fmaxf(m, tmax);
-    float corr = expf(m - mn);  // exp(-inf) = 0 on the first tile
+    const float mn = fmaxf(m, tmax);
+    const float corr = expf(m - mn);  // exp(-inf) = 0 on the first tile
     l *= corr;
 #pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] *= corr;
+    for (int d = 0; d < NC * 4; ++d) acc[d] *= corr;
 #pragma unroll
     for (int j = 0; j < ATT_KT; ++j) {
       if (j < nk) {
-        float p = expf(sc[j] - mn);
+        const float p = expf(sc[j] - mn);
         l += p;
 #pragma unroll
-        for (int d = 0; d < D; d += 4) {
-          float4 vv = *reinterpret_cast<const float4*>(&Vs[j][d]);
-          acc[d] += p * vv.x, acc[d + 1] += p * vv.y, acc[d + 2] += p * vv.z, acc[d + 3] += p * vv.w;
+        for (int i = 0; i < NC; ++i) {
+          const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][(4 * i + sub) * 4]);
+          acc[4 * i] += p * vv.x, acc[4 * i + 1] += p * vv.y, acc[4 * i + 2] += p * vv.z, acc[4 * i + 3] += p * vv.w;
         }
       }
     }
     m = mn;
   }
   if (active) {
-    float inv = 1.0f / l;
+    const float inv = 1.0f / l;
     OutT* o = out + (size_t)(st + qi) * ldo + h * D;
 #pragma unroll
-    for (int d = 0; d < D; ++d) put_out<OutT, SPLIT>(o + d, ldo / 2, acc[d] * inv);
+    for (int i = 0; i < NC; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) put_out<OutT, SPLIT>(o + (4 * i + sub) * 4 + e, ldo / 2, acc[4 * i + e] * inv);
   }
 }
 
@@ -335,8 +366,8 @@ extern "C" int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_o
                                      int io_bf16, void* out, int ldo, cudaStream_t stream) {
   PFPP_CHECK_ARG(qkv && seg_start && seg_len && out && heads > 0 && (head_dim == 64 || head_dim == 32));
   if (n_segments == 0 || max_len == 0) return PFPP_OK;
-  int threads = max_len >= 128 ? 128 : ((max_len + 31) / 32) * 32;
-  dim3 grid(pfpp_cdiv(max_len, threads), heads, n_segments);
+  const int threads = 4 * ATT_QPB;
+  dim3 grid(pfpp_cdiv(max_len, ATT_QPB), heads, n_segments);
   float scale = 1.0f / sqrtf((float)head_dim);
 #define PFPP_ATT_CASE(DD, TI, TO, SP)                                                                        \
   attn_varlen_kernel<DD, TI, TO, SP><<<grid, threads, 0, stream>>>((const TI*)qkv, ld, q_off, k_off, v_off, \
@@ -358,14 +389,20 @@ extern "C" int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_o
 // mean over the L tokens of each fragment (denoiser_transformer.py:141-142): [F*L, C] -> [F, C]
 template <typename OutT, bool SPLIT>
 __global__ void mean_pool_kernel(const float* __restrict__ h, int L, int C, OutT* __restrict__ out) {
-  int f = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int l = 0; l < L; ++l) s += h[((size_t)f * L + l) * C + c];
-    put_out<OutT, SPLIT>(out + (size_t)f * (SPLIT ? 2 * C : C) + c, C, s / (float)L);
+  const int f = blockIdx.x;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < L; ++l) {  // same summation order per channel as a scalar loop over l
+      const float4 v = *reinterpret_cast<const float4*>(h + ((size_t)f * L + l) * C + c);
+      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+    OutT* o = out + (size_t)f * (SPLIT ? 2 * C : C) + c;
+    put_out<OutT, SPLIT>(o, C, s.x / (float)L);
+    put_out<OutT, SPLIT>(o + 1, C, s.y / (float)L);
+    put_out<OutT, SPLIT>(o + 2, C, s.z / (float)L);
+    put_out<OutT, SPLIT>(o + 3, C, s.w / (float)L);
   }
 }
-
 extern "C" int pfpp_mean_pool(const float* h, int F, int L, int C, int out_bf16, void* out, cudaStream_t stream) {
   PFPP_CHECK_ARG(h && out);
   if (F == 0) return PFPP_OK;

@@ -326,8 +326,12 @@ class BatchRunner:
             starts = np.concatenate([[0], np.cumsum(counts)[:-1]]) * e.L
             ctx.loc[0].copy_(torch.arange(self.F, dtype=torch.int32) * e.L)
             ctx.loc[1].fill_(e.L)
-            ctx.glo[0].copy_(torch.as_tensor(starts.astype(np.int32)))
-            ctx.glo[1].copy_(torch.as_tensor((np.asarray(counts) * e.L).astype(np.int32)))
+            # global-attention segments longest first: a CTA's work grows with the square of its segment, and the
+            # grid is ~2 waves of one CTA per SM, so the long ones must not land in the last wave (the order of the
+            # segment list does not affect any result)
+            order = np.argsort(-np.asarray(counts), kind="stable")
+            ctx.glo[0].copy_(torch.as_tensor(starts[order].astype(np.int32)))
+            ctx.glo[1].copy_(torch.as_tensor((np.asarray(counts)[order] * e.L).astype(np.int32)))
             ctx.noise_all.copy_(noise_all)
             for name in ("x", "ref_pose", "ref_dev"):
                 cur, buf = getattr(self, name), getattr(ctx, name)

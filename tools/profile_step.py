@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--frags", type=int, default=0, help="0: num_parts ~ U{8..20}")
+    ap.add_argument("--chamfer", action="store_true", help="also run the Chamfer forward / backward kernels once (32 x 2048 points)")
     a = ap.parse_args()
     from puzzlefusion_plusplus_b200 import synthetic
     from puzzlefusion_plusplus_b200.engine import Engine
@@ -36,6 +37,13 @@ def main():
     out = run_batch(eng, objs, max_iters=a.iters, noise=PerObjectNoise(dev, list(range(a.batch)), a.steps), trajectory=False,
                     use_graph=False)
     m = object_metrics(out, objs, engine=eng)
+    if a.chamfer:
+        from puzzlefusion_plusplus_b200.chamfer import chamfer_distance
+        g = torch.Generator().manual_seed(0)
+        p1 = torch.rand(32, 2048, 3, generator=g).to(dev).requires_grad_(True)
+        p2 = torch.rand(32, 2048, 3, generator=g).to(dev).requires_grad_(True)
+        d1, d2 = chamfer_distance(p1, p2)
+        (d1.sum() + d2.sum()).backward()
     torch.cuda.synchronize()
     print("fragments per object", parts, "| merged away:", int(sum(parts) - out["part_valids"].sum()), "| metrics", m.mean(0).tolist())
 
