@@ -49,7 +49,7 @@ WORKLOADS = {
     "config3": dict(frags=(8, 20), points=1000, ddpm_steps=100, max_iters=6, merge=True, verify_last=False, batch=32,
                     accept_bias=-1.0, slots=6),
     "config2": dict(frags=20, points=1000, ddpm_steps=100, max_iters=1, merge=False, verify_last=True, batch=32,
-                    accept_bias=3.1, slots=1),
+                    accept_bias=3.1, slots=2),
     "config5": dict(frags=64, points=2000, ddpm_steps=250, max_iters=1, merge=False, verify_last=True, batch=8,
                     accept_bias=3.1, slots=1),
 }
@@ -308,7 +308,14 @@ class KernelProbe:
                 e0.record()
                 probe.orig(name, *args, **kw)
                 e1.record()
-                key = f"{name}[level {args[0]}]" if name == "pfpp_sa_fused" else name
+                # one entry per kernel instantiation / problem shape: set-abstraction level, GEMM (N, K)
+                key = name
+                if name == "pfpp_sa_fused":
+                    key = f"{name}[level {args[0]}]"
+                elif name in ("pfpp_gemm_bf16", "pfpp_gemm_bf16x3"):
+                    key = f"{name}[N={args[11]},K={args[12]}]"
+                elif name == "pfpp_attention_tc":
+                    key = f"{name}[{'local' if args[9] else 'global'}]"
                 r = probe.rec.setdefault(key, {"events": [], "flops": 0.0})
                 r["events"].append((e0, e1))
                 r["flops"] += algorithmic_flops(name, args)
@@ -560,7 +567,7 @@ def main():
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
                      "frac": kernels[dom]["tflops"] / peak if peak else None, "traffic": ncu_traffic(dom),
-                     "traffic_note": "DRAM bytes per launch (read + write), mean over the launches captured in profiles/*_full_summary.txt",
+                     "traffic_note": "DRAM bytes per launch (read + write) of this kernel in the committed ncu --set full capture of the same workload (profiles/r2_kernel_traffic.json)",
                      "peak_source": peak_src,
                      "avg_launch_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["share_of_ddpm_step"],
                      "whole_step": {"algorithmic_tflop_per_ddpm_step": step_flops / 1e12,
@@ -596,19 +603,12 @@ class _Null:
 
 
 def ncu_traffic(entry):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/*_full_summary.txt); None if there is no capture."""
-    fname = {"pfpp_sa_fused": "r1e_sa_full_summary.txt", "pfpp_gemm_bf16": "r1d_gemm_full_summary.txt",
-             "pfpp_attention_tc": "r1e_attention_full_summary.txt"}.get(entry.split("[")[0])
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+    `ncu --set full` capture of the same workload (profiles/r2_kernel_traffic.json, made from
+    profiles/r2_full_summary.txt); None if that kernel / shape was not captured."""
     try:
-        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot, n = 0.0, 0
-        for ln in open(os.path.join(ROOT, "profiles", fname)):
-            f = ln.split()
-            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(f[1]) * unit[f[2].strip("[]")]
-                n += f[0] == "dram__bytes_read.sum"
-        return tot / n if n else None
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")))
+        return t[entry]["dram_bytes_per_launch"]
     except Exception:
         return None
 
