@@ -387,6 +387,7 @@ class BatchRunner:
              1, self.noise_all.data_ptr(), self.noise_all.stride(0), self.ref_dev.data_ptr(), self.ref_pose.data_ptr(),
              self.F, self.x.data_ptr(), hist.data_ptr(), hist.stride(0))
         call("pfpp_step_advance", self.step_ctr.data_ptr())
+        self._last_latent = latent
         return eps
 
     # -- phase 2 ---------------------------------------------------------------------------------
@@ -422,7 +423,7 @@ class BatchRunner:
             eps = self._launch_step()
             if self.record is not None:
                 self.record.append({"t": self.timesteps[self.si], "eps": eps[:, :7].clone(), "x": self.x.clone(),
-                                    "frag_slot": self.frag_slot.clone()})
+                                    "frag_slot": self.frag_slot.clone(), "latent": self._last_latent.clone()})
         self.si += 1
 
     # -- phase 3 ---------------------------------------------------------------------------------

@@ -136,8 +136,16 @@ def free_running(engine, obj, normals, steps, verify):
     xs = torch.stack([r["x"].cpu()[:n] for r in rec if "t" in r])
     xo = torch.stack([r["x"][:n] for r in steps])
     per_step = (xs - xo).abs().amax((1, 2))
+    # first DDPM step at which a VQ code of the free-running engine differs from the oracle's: from there on the two
+    # runs are different (equally valid) trajectories, and the pose difference is no longer a rounding error
+    flips = [float(((r["latent"].cpu().reshape(n, 100, 16) - o["latent"][:n].reshape(n, 100, 16)).abs().amax(-1) > 1e-6).sum())
+             for r, o in zip([r for r in rec if "t" in r], steps)]
+    first_flip = next((i for i, f in enumerate(flips) if f > 0), -1)
+    before = per_step[:first_flip] if first_flip >= 0 else per_step
     res = {"pose_final": float(per_step[-1]), "pose_max_over_steps": float(per_step.max()),
-           "first_step_over_1e-4": int((per_step > 1e-4).nonzero()[0]) if bool((per_step > 1e-4).any()) else -1}
+           "first_step_over_1e-4": int((per_step > 1e-4).nonzero()[0]) if bool((per_step > 1e-4).any()) else -1,
+           "first_code_flip_step": first_flip, "codes_flipped_at_that_step": int(flips[first_flip]) if first_flip >= 0 else 0,
+           "pose_max_before_first_flip": float(before.max()) if len(before) else 0.0}
     v = [r for r in rec if r.get("verify")]
     if v and verify is not None:
         P = engine.P
@@ -151,7 +159,8 @@ def free_running(engine, obj, normals, steps, verify):
     return res
 
 
-def report(modes=("fp32", "tc32", "bf16"), T=100, frags=20, points=1000, seed=2000, oracle_device="cpu", log=print):
+def report(modes=("fp32", "tc32", "bf16"), T=100, frags=20, points=1000, seed=2000, oracle_device="cpu", log=print,
+           extra_seeds=()):
     from puzzlefusion_plusplus_b200 import synthetic
     from puzzlefusion_plusplus_b200.engine import Engine
     ckpt = synthetic.make_checkpoints(0)
@@ -174,8 +183,122 @@ def report(modes=("fp32", "tc32", "bf16"), T=100, frags=20, points=1000, seed=20
             f"VQ codes equal {100 * tf['code_match']:.3f} % (worst step {100 * tf['code_match_min']:.2f} %, "
             f"{tf['steps_with_any_flip']} of {len(steps)} steps with a flip); FPS centroids equal {100 * tf['fps_centroid_match']:.3f} %")
         log(f"[{mode}] free-running: final pose err {fr['pose_final']:.2e}, max over steps {fr['pose_max_over_steps']:.2e}, "
-            f"first step over 1e-4: {fr['first_step_over_1e-4']}; logits {fr.get('logit_max', float('nan')):.2e}, "
-            f"edge features {fr.get('feature_max', float('nan')):.2e}, decisions equal {fr.get('decisions_equal')}")
+            f"first step over 1e-4: {fr['first_step_over_1e-4']}, first VQ-code flip at step {fr['first_code_flip_step']} "
+            f"({fr['codes_flipped_at_that_step']} of {frags * 100} codes), max pose err before it {fr['pose_max_before_first_flip']:.2e}; "
+            f"logits {fr.get('logit_max', float('nan')):.2e}, edge features {fr.get('feature_max', float('nan')):.2e}, "
+            f"decisions equal {fr.get('decisions_equal')}")
+        del eng
+    # free-running statistics over more objects / noise draws (oracle on the GPU: eager fp32, TF32 off)
+    if extra_seeds:
+        from puzzlefusion_plusplus_b200.engine import Engine as _E
+        stats = {m: [] for m in modes}
+        for sd_ in extra_seeds:
+            o2 = synthetic.make_object(sd_, num_parts=frags, n_points=points)
+            g2 = torch.Generator().manual_seed(sd_)
+            n2 = [torch.randn(1, 20, 7, generator=g2) for _ in range(T + 1)]
+            rec2 = oracle_run(ckpt, o2, T, n2, "cuda")
+            st2 = [r for r in rec2 if "t" in r]
+            v2 = next((r for r in rec2 if r.get("verify")), None)
+            for mode in modes:
+                eng = _E(ckpt, num_inference_steps=T, precision=mode, device=DEV)
+                fr = free_running(eng, o2, n2, st2, v2)
+                stats[mode].append(fr)
+                log(f"[{mode}] seed {sd_} (oracle on the GPU): final pose err {fr['pose_final']:.2e}, first flip at step "
+                    f"{fr['first_code_flip_step']}, max before it {fr['pose_max_before_first_flip']:.2e}, decisions equal "
+                    f"{fr.get('decisions_equal')}")
+                del eng
+        out["free_running_more_seeds"] = {"seeds": list(extra_seeds), "oracle": "cuda eager fp32, TF32 off", **stats}
+    return out
+
+
+def loop_report(modes=("fp32", "tc32"), parts=(20, 16, 12, 9), T=100, max_iters=6, seed=4100, log=print):
+    """BASELINE config 3's loop at full length -- T = 100 DDPM steps per outer iteration, up to 6 iterations with
+    verify / promote / merge and early exits, B objects of up to 20 fragments in ONE packed batch -- against the
+    oracle run object by object as eager fp32 PyTorch on the GPU (TF32 off; how the reference itself would run).
+    Returns per mode and object: agreement of the agglomeration decisions, pose / trajectory errors."""
+    from oracle import loop as ol
+    from oracle import third_party as tp
+    from puzzlefusion_plusplus_b200 import _lib, synthetic
+    from puzzlefusion_plusplus_b200.engine import Engine
+    from puzzlefusion_plusplus_b200.loop import BatchRunner, run_interleaved
+    no_tf32()
+    ckpt = synthetic.make_checkpoints(0, accept_bias=-1.0)
+    objs = [synthetic.make_object(seed + i, num_parts=n) for i, n in enumerate(parts)]
+    noises = []
+    for i in range(len(objs)):
+        g = torch.Generator().manual_seed(seed + 100 + i)
+        noises.append(([torch.randn(1, 20, 7, generator=g) for _ in range(1 + max_iters * (T - 1))],
+                       [torch.rand(1, generator=g) for _ in range(40)]))
+
+    def fps_batched(xyz, n_samples, start=None):
+        K, N, _ = xyz.shape
+        x = xyz.contiguous().float()
+        idx = torch.empty(K, n_samples, dtype=torch.int32, device=x.device)
+        st = None if start is None else start.to(torch.int32).to(x.device).contiguous()
+        if N <= 4096:
+            _lib.call("pfpp_fps", x.data_ptr(), K, N, n_samples, None if st is None else st.data_ptr(), idx.data_ptr(), None)
+        else:  # merged clouds: the ragged kernel (one cloud)
+            meta = torch.tensor([0, N, n_samples, int(st[0]) if st is not None else 0, 0], dtype=torch.int32, device=x.device)
+            dist = torch.empty(N, device=x.device)
+            mp = meta.data_ptr()
+            _lib.call("pfpp_fps_ragged", x.data_ptr(), mp, mp + 4, mp + 8, mp + 12, 1, dist.data_ptr(), mp + 16, idx.data_ptr())
+        return idx.to(torch.int64)
+    saved = tp.fps_batched
+    tp.fps_batched = fps_batched
+    refs = []
+    t0 = time.perf_counter()
+    try:
+        sd = {k: {n: t.to(DEV) for n, t in v.items()} for k, v in ckpt.items()}
+        for o, (normals, uniforms) in zip(objs, noises):
+            od_ = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in o.items()}
+            od_["correspondences"] = [c.to(DEV) for c in o["correspondences"]]
+            with torch.device(DEV), torch.no_grad():
+                r = ol.run_object(sd["encoder"], sd["denoiser"], sd["verifier"], od_, T, max_iters,
+                                  rng=ol.ReplayRNG([n.to(DEV) for n in normals], [u.to(DEV) for u in uniforms]))
+            refs.append({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in r.items()})
+    finally:
+        tp.fps_batched = saved
+    torch.cuda.synchronize()
+    log(f"oracle (eager fp32 on the GPU): {len(objs)} objects in {time.perf_counter() - t0:.1f} s, iterations {[r['iters'] for r in refs]}, "
+        f"merged fragments {[int(sum(r['graph'].nodes[i]['pivot'] != i for i in range(n))) for r, n in zip(refs, parts)]}")
+
+    class PerObjectReplay:
+        def __init__(self):
+            self.n = [list(n) for n, _ in noises]
+            self.u = [list(u) for _, u in noises]
+
+        def initial(self, B, P):
+            return torch.cat([self.n[b].pop(0) for b in range(B)]).to(DEV)
+
+        def iteration_noise(self, B, P, timesteps, active=None):
+            rows = []
+            for t in timesteps:
+                rows.append(torch.cat([self.n[b].pop(0) if (t > 0 and (active is None or b in active)) else torch.zeros(1, P, 7)
+                                       for b in range(B)]))
+            return torch.stack(rows).reshape(len(timesteps), B * P, 7).to(DEV).contiguous()
+
+        def fps_uniform(self, b):
+            return self.u[b].pop(0).to(torch.float32).reshape(1).to(DEV)
+
+    out = {"config": f"objects of {list(parts)} fragments x 1000 points, T = {T}, max_iters = {max_iters}, merges on"}
+    for mode in modes:
+        eng = Engine(ckpt, num_inference_steps=T, precision=mode, device=DEV)
+        r = BatchRunner(eng, objs, max_iters=max_iters, noise=PerObjectReplay(), trajectory=True)
+        res = run_interleaved([r])[0]
+        rows = []
+        for b, (ref, n) in enumerate(zip(refs, parts)):
+            piv_ref = [ref["graph"].nodes[i]["pivot"] for i in range(n)]
+            same = (res["pivots"][b] == piv_ref and torch.equal(res["ref_part"][b], ref["ref_part"]) and res["iters"][b] == ref["iters"])
+            row = {"fragments": n, "iterations": ref["iters"], "merged": int(sum(p != i for i, p in enumerate(piv_ref))),
+                   "decisions_equal": bool(same)}
+            if same:
+                valid = ref["part_valids"] > 0
+                row["pose_err"] = float((res["x"][b][valid] - ref["x"][valid]).abs().max())
+                row["pred_trans_err"] = float((res["pred_trans"][b, :n] - ref["pred_trans"][:n]).abs().max())
+                row["trajectory_err"] = float((res["trajectory"][b] - ref["trajectory"][:, :n]).abs().max())
+            rows.append(row)
+            log(f"[{mode}] object {b}: {row}")
+        out[mode] = rows
         del eng
     return out
 
@@ -189,7 +312,15 @@ if __name__ == "__main__":
     ap.add_argument("--seed", type=int, default=2000)
     ap.add_argument("--oracle-device", default="cpu")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--extra-seeds", default="", help="comma-separated object seeds for more free-running runs (GPU oracle)")
+    ap.add_argument("--loop", action="store_true", help="the full config-3 loop (T = 100, max_iters = 6, merges) instead")
     a = ap.parse_args()
-    r = report(tuple(a.modes.split(",")), a.steps, a.frags, a.points, a.seed, a.oracle_device)
+    if a.loop:
+        r = loop_report(tuple(m for m in a.modes.split(",") if m != "bf16") or ("fp32",))
+        if a.json:
+            json.dump(r, open(a.json, "w"), indent=1)
+        sys.exit(0)
+    r = report(tuple(a.modes.split(",")), a.steps, a.frags, a.points, a.seed, a.oracle_device,
+               extra_seeds=tuple(int(x) for x in a.extra_seeds.split(",") if x))
     if a.json:
         json.dump(r, open(a.json, "w"), indent=1)
