@@ -9,8 +9,9 @@ A "step" is one pass of the hot path over one batch of synthetic objects.  Workl
   config3 (default, the BASELINE metric: "full auto-aggl loop"): 32 DISTINCT objects per GPU with
           num_parts ~ U{8..20}, 1000 points per fragment, 100 DDPM steps per outer iteration, max_iters = 6 outer
           denoise -> verify -> merge iterations with merges and early exits on (auto_aggl.py:136-289), a new noise
-          seed for every object of every step.  With N GPUs this is BASELINE config 4: 32*N objects dealt to the ranks
-          by the package's own `sharding.shard_objects`, metrics gathered with `sharding.gather_metrics`.
+          seed for every object of every step.  With N GPUs this is BASELINE config 4: 32*N objects (N noise-independent
+          copies of the 32 geometries: fixed work per GPU) dealt to the ranks by the package's own
+          `sharding.shard_objects`, metrics gathered with `sharding.gather_metrics`.
   config2: 32 objects x 20 fragments, one denoise pass (100 DDPM steps) + one verifier pass, no merge; also measured
           as the `secondary` key of the default run.
   config5: 64 fragments x 2000 points, 250 DDPM steps, 8 objects in flight.
@@ -351,12 +352,20 @@ class Arm:
                             chunk_frags=a.chunk, max_parts=P, freeze_gc=True)
         self.engines = [mk() for _ in range(self.n_slots)]
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.n_slots)]
-        # the global batch of world*batch distinct objects, dealt by the package's sharding (serpentine by fragment count)
+        # Weak scaling: the global batch is `world` copies of the same heterogeneous set of `batch` object geometries
+        # (every copy runs on its own noise, so its outer-iteration dynamics differ), dealt to the ranks by the package's
+        # sharding (serpentine by fragment count): every rank gets the same multiset of fragment counts, i.e. the same
+        # expected work as the single-GPU run.
         total = w["batch"] * world
-        parts = object_parts(w, total)
+        parts = object_parts(w, w["batch"]) * world
         self.mine = sharding.shard_objects(parts, rank, world)
         self.total = total
-        self.objects = [synthetic.make_object(2000 + i, num_parts=parts[i], n_points=w["points"], max_parts=P) for i in self.mine]
+        geo = {}
+        for i in self.mine:
+            j = i % w["batch"]
+            if j not in geo:
+                geo[j] = synthetic.make_object(2000 + j, num_parts=parts[i], n_points=w["points"], max_parts=P)
+        self.objects = [geo[i % w["batch"]] for i in self.mine]
         self.frag_iters, self.obj_iters, self.n_obj_done = 0, 0, 0
 
     def seeds(self, k):
@@ -385,6 +394,9 @@ class Arm:
             runners[k] = r
             return r
         outs = run_pipelined(self.engines, self.streams, mk, n)
+        # this rank's own work ends here; what follows (metric block + all-gather) synchronises the ranks
+        self.ev_work_done = torch.cuda.Event(enable_timing=True)
+        self.ev_work_done.record()
         gathered = []
         for k in range(n):
             m = object_metrics(outs[k], self.objects, engine=self.engines[0]).to(self.dev)  # [B,4] per-object metrics
@@ -446,7 +458,7 @@ def main():
         t = torch.tensor([elapsed_ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        busy_ms, elapsed_ms = elapsed_ms, float(t.item())
+        busy_ms, elapsed_ms = e0.elapsed_time(arm.ev_work_done), float(t.item())  # per-rank time of the loop itself
         value = B * world * steps / (elapsed_ms * 1e-3)
         if not e2e:
             return value, None, elapsed_ms, launches, busy_ms
@@ -560,7 +572,8 @@ def main():
                    "outer_iterations_per_object": round(iters_mean, 3),
                    "fragment_iterations_per_object": round(stats["fragment_iterations_per_object"], 2),
                    "sharding": "puzzlefusion_plusplus_b200.sharding.shard_objects / gather_metrics",
-                   "rank_busy_ms": [round(b, 1) for b in busy_all],
+                   "rank_busy_ms": [round(b, 1) for b in busy_all],  # loop time per rank before the metric all-gathers
+                   "rank_imbalance": round(max(busy_all) / (sum(busy_all) / len(busy_all)), 4),
                    "l2": "per-step working set (activations of one batch) exceeds L2; new noise seeds every step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
