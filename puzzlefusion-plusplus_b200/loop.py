@@ -1,11 +1,19 @@
 """The auto-agglomerative denoise -> verify -> merge loop for a BATCH of fractured objects.
 
 Generalises AutoAgglomerative.test_step (puzzlefusion_plusplus/auto_aggl.py:95-319, batch size 1 in the
-reference) to B objects advanced in lock-step on one GPU: the per-DDPM-step work of all valid fragments
-of all active objects is one packed launch sequence (engine.py); the verify stage is one batched
-edge-histogram + verifier pass per outer iteration; the tiny agglomeration-graph state (pivots,
-accumulated init poses, reference flags -- auto_aggl.py:122-131,208-289) stays on the host exactly as in
-the reference, with ONE device->host read per outer iteration instead of one per DDPM step.
+reference) to B objects advanced in lock-step on one GPU:
+
+  * one DDPM step of all valid fragments of all active objects = ONE C call (pfpp_denoiser_step), captured once per
+    batch geometry in a CUDA graph and replayed T times with a device-side step counter;
+  * reference parts keep their pose for a whole outer iteration (auto_aggl.py:150), so they are encoded once per
+    iteration and only the other fragments are re-encoded every step (bit-identical results);
+  * the verify stage is one batched edge-histogram + verifier pass per outer iteration, followed by the ONE
+    device->host read of that iteration (poses, logits, history, the previous merges' centroids / scales);
+  * the tiny agglomeration-graph state (pivots, accumulated init poses, reference flags -- auto_aggl.py:122-131,
+    208-289) stays on the host exactly as in the reference; the merge stage of all components of all objects is one
+    asynchronous pfpp_merge call whose results are read back with the next iteration's poses;
+  * run_pipelined keeps several batches in flight (one Engine + stream each) so that the late, nearly empty outer
+    iterations of one batch run under the full early iterations of the next.
 
 Every reference quirk listed in SURVEY.md Appendix C is preserved (un-normalised quaternion for the
 by-area cloud, no re-noising between outer iterations, index-aligned Chamfer in the merge filter, ...).
@@ -253,11 +261,12 @@ class BatchRunner:
     """One batch advanced through the loop in three phases per outer iteration so that several runners
     (each on its own CUDA stream) can be interleaved by one host thread:
         begin_iteration() -> step() x T -> end_iteration()
-    The T DDPM steps of an iteration share one launch sequence whose only step-dependent inputs (AdaLN
-    row, scheduler coefficients, noise row, history row) are indexed by a DEVICE-side step counter; with
-    ``use_graph`` the sequence runs over the persistent buffers of a StepContext and is captured once per batch
-    geometry (after an eager first step that also sizes the workspaces); every later iteration / batch of the same
-    geometry replays the cached graph from its first step on."""
+    The T DDPM steps of an iteration share one launch sequence (one pfpp_denoiser_step call) whose only
+    step-dependent inputs (AdaLN row, scheduler coefficients, noise row, history row) are indexed by a DEVICE-side
+    step counter; with ``use_graph`` the call runs over the persistent buffers of a StepContext and is captured once
+    per batch geometry (after an eager first step that also sizes the workspaces); every later iteration / batch of
+    the same geometry replays the cached graph from its first step on.  ``record`` (a list) switches to the
+    kernel-by-kernel launch sequence of engine.py and collects per-step eps / poses / latents (parity tests)."""
 
     def __init__(self, engine, objects=None, max_iters=1, threshold=0.9, noise=None, merge=True, record=None,
                  trajectory=True, state=None, verify_last=False, use_graph=True):
