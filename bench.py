@@ -52,7 +52,7 @@ WORKLOADS = {
     "config2": dict(frags=20, points=1000, ddpm_steps=100, max_iters=1, merge=False, verify_last=True, batch=32,
                     accept_bias=3.1, slots=2),
     "config5": dict(frags=64, points=2000, ddpm_steps=250, max_iters=1, merge=False, verify_last=True, batch=8,
-                    accept_bias=3.1, slots=1),
+                    accept_bias=3.1, slots=2),
 }
 STATS_FILE = os.path.join(ROOT, "profiles", "r2_config3_workload_stats.json")
 

@@ -205,3 +205,19 @@ def test_batch_state_matching_tables_cached_per_object():
     n_pairs1 = int(a.e_len[:e1].sum())
     assert torch.equal(a.pair_src[:n_pairs1] + o2["part_pcs_by_area"].shape[0], b.pair_src[-n_pairs1:])
     assert n1 > 0
+
+
+def test_bench_weak_scaling_deal_gives_every_rank_the_same_fragment_counts():
+    """bench.py's config-4 workload: `world` copies of the 32 geometries dealt by sharding.shard_objects -> every rank
+    owns 32 objects with the same multiset of fragment counts (fixed work per GPU), every object exactly once."""
+    import bench
+    from puzzlefusion_plusplus_b200 import sharding
+    w = dict(bench.WORKLOADS["config3"])
+    base = bench.object_parts(w, w["batch"])
+    assert len(base) == 32 and min(base) >= 8 and max(base) <= 20 and len(set(base)) > 4
+    for world in (1, 2, 8):
+        parts = base * world
+        owned = [sharding.shard_objects(parts, r, world) for r in range(world)]
+        assert sorted(i for o in owned for i in o) == list(range(32 * world))
+        for o in owned:
+            assert len(o) == 32 and sorted(parts[i] for i in o) == sorted(base)
