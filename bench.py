@@ -394,6 +394,7 @@ class Arm:
             runners[k] = r
             return r
         outs = run_pipelined(self.engines, self.streams, mk, n)
+        self.host = getattr(run_pipelined, "last_host", None)
         # this rank's own work ends here; what follows (metric block + all-gather) synchronises the ranks
         self.ev_work_done = torch.cuda.Event(enable_timing=True)
         self.ev_work_done.record()
@@ -572,6 +573,10 @@ def main():
                    "outer_iterations_per_object": round(iters_mean, 3),
                    "fragment_iterations_per_object": round(stats["fragment_iterations_per_object"], 2),
                    "sharding": "puzzlefusion_plusplus_b200.sharding.shard_objects / gather_metrics",
+                   "host_thread": (None if not getattr(arm, "host", None) else
+                                   {"busy_frac": round(1.0 - arm.host["idle_s"] / max(arm.host["total_s"], 1e-9), 3),
+                                    "note": "share of the scheduling thread's time NOT spent waiting for the device "
+                                            "(last run_pipelined call = the e2e leg)"}),
                    "rank_busy_ms": [round(b, 1) for b in busy_all],  # loop time per rank before the metric all-gathers
                    "rank_imbalance": round(max(busy_all) / (sum(busy_all) / len(busy_all)), 4),
                    "l2": "per-step working set (activations of one batch) exceeds L2; new noise seeds every step"},

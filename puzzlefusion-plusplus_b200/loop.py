@@ -598,17 +598,23 @@ def run_pipelined(engines, streams, make_runner, n_batches, poll_s=2e-4):
             ev.record()
             events[i] = ev
 
+    t_begin = time.perf_counter()
+    idle = 0.0
     for i in range(n):
         advance(i)
     while any(ev is not None for ev in events):
         ready = [i for i, ev in enumerate(events) if ev is not None and ev.query()]
         if not ready:
+            t0 = time.perf_counter()
             time.sleep(poll_s)
+            idle += time.perf_counter() - t0
             continue
         i = ready[0]
         with torch.cuda.stream(streams[i]):
             slots[i].end_iteration()
         advance(i)
+    # host-side accounting of the last call (seconds): total, and the part spent waiting for the device
+    run_pipelined.last_host = {"total_s": time.perf_counter() - t_begin, "idle_s": idle}
     for s_ in streams:
         cur.wait_stream(s_)
     return results
