@@ -157,6 +157,15 @@ int pfpp_layernorm(const float* x, const float* residual, const float* gamma, co
                    const int* row_group, int rows_per_group, long long rows, int C, int out_bf16, void* y,
                    float* sum_out, cudaStream_t stream);
 
+/* Residual projection fused with the (Ada)LayerNorm that follows it (attention.py:75-92 -- diffusers Attention.to_out /
+ * FeedForward.net[2] + residual -- then MyAdaLayerNorm attention.py:5-25 or norm3):
+ *   h[M,512] += A[M,K] W[512,K]^T + bias  (fp32, in place);  ln_out[M,512] (bf16) = LN(h) modulated like pfpp_layernorm
+ * (mod / row_group / rows_per_group, or gamma / beta when mod == NULL).  bf16 operands, tcgen05 CTA pairs, one CTA per
+ * 128 full rows (the 128 x 512 fp32 accumulator fills tensor memory).  K % 8 == 0. */
+int pfpp_gemm_res_ln(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int M, int K,
+                     const float* mod, const int* row_group, int rows_per_group, const float* gamma, const float* beta,
+                     void* ln_out, cudaStream_t stream);
+
 /* F.scaled_dot_product_attention with the reference's masks (diffusers AttnProcessor2_0 at
  * attention.py:79,84; torch MultiheadAttention at verifier_transformer.py:62) expressed as
  * full attention inside packed segments. head_dim in {32,64}. */
@@ -291,6 +300,7 @@ typedef struct PfppDenoiserLayer {
 typedef struct PfppDenoiserWeights {
   int mode, C, heads, n_layers, P, L, latent_dim, T;
   int tc_attention, local_tiles; /* mode 1: tcgen05 attention; 125-token tiles per local-attention CTA */
+  int fused_ln; /* mode 1: out-proj / FF2 + residual + the following (Ada)LayerNorm as ONE kernel (pfpp_gemm_res_ln) */
   PfppLinear shape_embedding, param_fc;
   const float* ref_emb; /* [2, C] */
   const float* pe;      /* [P, C] */

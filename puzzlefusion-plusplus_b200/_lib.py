@@ -39,6 +39,7 @@ SIGNATURES = {
     "pfpp_embed_features": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P],
     "pfpp_combine_embed": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     "pfpp_layernorm": [_P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _P, _P, _P],
+    "pfpp_gemm_res_ln": [_P, _I, _P, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P],
     "pfpp_attention_varlen": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     "pfpp_attention_tc": [_P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P],
     "pfpp_attention_tc_trace": [_P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P],
@@ -89,7 +90,7 @@ class PfppDenoiserLayer(ctypes.Structure):
 
 class PfppDenoiserWeights(ctypes.Structure):
     _fields_ = [("mode", _I), ("C", _I), ("heads", _I), ("n_layers", _I), ("P", _I), ("L", _I), ("latent_dim", _I),
-                ("T", _I), ("tc_attention", _I), ("local_tiles", _I), ("shape_embedding", PfppLinear),
+                ("T", _I), ("tc_attention", _I), ("local_tiles", _I), ("fused_ln", _I), ("shape_embedding", PfppLinear),
                 ("param_fc", PfppLinear), ("ref_emb", _P), ("pe", _P), ("mod", _P), ("coef", _P),
                 ("layers", PfppDenoiserLayer * MAX_LAYERS), ("head0", PfppLinear), ("head_t2", PfppLinear),
                 ("head_r2", PfppLinear), ("head_t4", PfppLinear), ("head_r4", PfppLinear)]

@@ -289,12 +289,6 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t* v, floa
 // [32 x 128 B] box in its private shared-memory tile and hands the box to the TMA engine
 // (cp.async.bulk.tensor store): the SM issues no global stores at all and the write is full-line.
 // NCH = accumulator chunks (32 columns each) feeding one 64-column output slab: 2, or 4 for GEGLU.
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
-               "r"(c1)
-               : "memory");
-}
-
 template <int EPI>
 __device__ __forceinline__ void epilogue_slab_tma(uint32_t taddr, int acc_col0, uint8_t* stage, uint32_t stage_addr, int lane,
                                                   int row0, int out_col0, int n_acc0, int N, const float* __restrict__ bias,
@@ -457,16 +451,6 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
                "h"(cta_mask)
                : "memory");
 }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 constexpr int T2_THREADS = 64 + 256;
 
 // MC = true: CTAs run as clusters of 2 that own vertically adjacent 128-row tiles of the same 256-column block.
@@ -613,41 +597,6 @@ constexpr uint32_t T3_HALF_BYTES = 128 * TC_BK * 2;            // one [128 x 64]
 constexpr uint32_t T3_STAGE_BYTES = 2 * T3_HALF_BYTES;          // A half + W half per CTA
 constexpr uint32_t T3_SMEM_BYTES = T3_STAGES * T3_STAGE_BYTES + T2_EPI_STAGE_BYTES + 1024 + 256;
 constexpr uint32_t T3_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;                 // clears the CTA-rank bit of a shared::cluster address
-
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta_rank) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
-      "}" ::"r"(local_bar),
-      "r"(cta_rank)
-      : "memory");
-}
-
 template <int EPI, int OUT>
 __global__ void __launch_bounds__(T2_THREADS)
     gemm_bf16_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,

@@ -232,11 +232,15 @@ int run_denoiser(const PfppDenoiserWeights* w, const float* x, const float* scal
   if (tc_local) {
     local_segments_kernel<<<pfpp_cdiv(d.n_loc, 128), 128, 0, s>>>(d.n_loc, 5 * w->local_tiles * L, M, d.loc_start, d.loc_len);
   }
+  // bf16 mode: the residual projections (out-proj, FF2) also emit the NEXT (Ada)LayerNorm's output (pfpp_gemm_res_ln):
+  // 17 of the 18 LayerNorm passes of a step and one read of the residual stream per sub-layer disappear
+  const bool fuse = mode == 1 && w->fused_ln && C == 512;
   for (int li = 0; li < w->n_layers; ++li) {
     const PfppDenoiserLayer& lw = w->layers[li];
     for (int which = 0; which < 2; ++which) {
       const float* mod = w->mod + (size_t)(li * 2 + which) * w->T * 2 * C;
-      PF(pfpp_layernorm(d.h, nullptr, nullptr, nullptr, mod, frag_step, L, M, C, mode, d.ln, nullptr, s));
+      if (!fuse || (li == 0 && which == 0))
+        PF(pfpp_layernorm(d.h, nullptr, nullptr, nullptr, mod, frag_step, L, M, C, mode, d.ln, nullptr, s));
       PF(gemm(mode, d.ln, C, lw.qkv[which], d.qkv, 3 * C, M, PFPP_EPI_NONE, nullptr, 0, mode != 2, s));
       if (which == 1 && tc_global) {
         PF(pfpp_attention_tc(d.qkv, M, 3 * C, C, obj_seg_start, obj_seg_len, n_obj, max_global, H, 0, d.ao, C, s));
@@ -249,11 +253,24 @@ int run_denoiser(const PfppDenoiserWeights* w, const float* x, const float* scal
         PF(pfpp_attention_varlen(d.qkv, 3 * C, 0, C, 2 * C, obj_seg_start, obj_seg_len, n_obj, max_global, H, D, mode, d.ao,
                                  wm * C, s));
       }
-      PF(gemm(mode, d.ao, C, lw.out[which], d.h, C, M, PFPP_EPI_NONE, d.h, C, false, s));
+      if (fuse && which == 0) {  // -> AdaLN of the global attention
+        PF(pfpp_gemm_res_ln(d.ao, C, lw.out[0].w, lw.out[0].k, lw.out[0].bias, d.h, M, lw.out[0].k, mod + (size_t)w->T * 2 * C,
+                            frag_step, L, nullptr, nullptr, d.ln, s));
+      } else if (fuse) {         // -> norm3
+        PF(pfpp_gemm_res_ln(d.ao, C, lw.out[1].w, lw.out[1].k, lw.out[1].bias, d.h, M, lw.out[1].k, nullptr, nullptr, 0,
+                            lw.norm3_w, lw.norm3_b, d.ln, s));
+      } else {
+        PF(gemm(mode, d.ao, C, lw.out[which], d.h, C, M, PFPP_EPI_NONE, d.h, C, false, s));
+      }
     }
-    PF(pfpp_layernorm(d.h, nullptr, lw.norm3_w, lw.norm3_b, nullptr, nullptr, 0, M, C, mode, d.ln, nullptr, s));
+    if (!fuse) PF(pfpp_layernorm(d.h, nullptr, lw.norm3_w, lw.norm3_b, nullptr, nullptr, 0, M, C, mode, d.ln, nullptr, s));
     PF(gemm(mode, d.ln, C, lw.ff1, d.ff, 4 * C, M, PFPP_EPI_GEGLU, nullptr, 0, true, s));
-    PF(gemm(mode, d.ff, 4 * C, lw.ff2, d.h, C, M, PFPP_EPI_NONE, d.h, C, false, s));
+    if (fuse && li + 1 < w->n_layers) {  // -> AdaLN of the next layer's local attention
+      PF(pfpp_gemm_res_ln(d.ff, 4 * C, lw.ff2.w, lw.ff2.k, lw.ff2.bias, d.h, M, lw.ff2.k,
+                          w->mod + (size_t)((li + 1) * 2) * w->T * 2 * C, frag_step, L, nullptr, nullptr, d.ln, s));
+    } else {
+      PF(gemm(mode, d.ff, 4 * C, lw.ff2, d.h, C, M, PFPP_EPI_NONE, d.h, C, false, s));
+    }
   }
   if (mode == 0) {
     PF(pfpp_mean_pool(d.h, F, L, C, 0, d.pooled, s));

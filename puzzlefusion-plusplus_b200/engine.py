@@ -78,6 +78,7 @@ class Engine:
         self.tc_attention = True  # tcgen05 attention in bf16 mode (segments > 512 tokens stream K/V through a ring)
         self.fused_sa = True     # fused gather + 3-layer MLP + max tcgen05 kernel in bf16 mode
         self.local_tiles = 4     # 125-token tiles (5 fragments) per local-attention CTA, two per softmax group
+        self.fused_ln = True     # bf16 mode: out-proj / FF2 + residual + next (Ada)LayerNorm in one kernel
         self.coarse = True       # run the stages through the coarse C entry points (pfpp_encoder_forward, ...)
         # Reference parts keep their pose for a whole outer iteration (clamped every step, auto_aggl.py:150), so their
         # encoder output is the same at every DDPM step: encode them once per iteration, re-encode only the others.
@@ -126,6 +127,7 @@ class Engine:
         wd.mode, wd.C, wd.heads, wd.n_layers, wd.P, wd.L = m, self.C, self.heads, len(w.layers), self.P, self.L
         wd.latent_dim, wd.T = self.latent_dim, self.T
         wd.tc_attention, wd.local_tiles = int(self.tc_attention), self.local_tiles
+        wd.fused_ln = int(self.fused_ln)
         wd.shape_embedding, wd.param_fc = self._lin(w.shape_embedding, m), self._lin(w.param_fc, m)
         wd.ref_emb, wd.pe, wd.mod, wd.coef = w.ref_emb.data_ptr(), w.pe.data_ptr(), w.mod.data_ptr(), self.coef.data_ptr()
         for i, lw in enumerate(w.layers):
@@ -155,6 +157,7 @@ class Engine:
         """the kernel-selection switches may be flipped between calls (tests, tools): mirror them into the structs"""
         self.cw_enc.fused_sa = int(self.fused_sa)
         self.cw_den.tc_attention, self.cw_den.local_tiles = int(self.tc_attention), self.local_tiles
+        self.cw_den.fused_ln = int(self.fused_ln)
 
     def step_kernels(self, F):
         """kernels one DDPM step launches (bench.py's gpu_launches; the coarse entry points launch whole sequences)"""
@@ -422,12 +425,27 @@ class Engine:
         loc_start, loc_len = seg_local
         glo_start, glo_len = seg_global
         n_obj = glo_start.numel()
+        # bf16 mode: the residual projections (out-proj, FF2) also emit the NEXT (Ada)LayerNorm's output (pfpp_gemm_res_ln)
+        fuse = self.bf16 and self.fused_ln and C == 512
+        n_layers = len(w.layers)
+
+        def res_proj(a, lda, lin, nxt):
+            """h += a W^T + b; nxt = None | ("mod", table) | ("affine", gamma, beta): the LayerNorm that follows."""
+            if fuse and nxt is not None:
+                ada = nxt[0] == "mod"
+                call("pfpp_gemm_res_ln", a.data_ptr(), lda, lin.w16.data_ptr(), lin.k16, _lib.ptr(lin.b), h.data_ptr(), M,
+                     lin.k16, nxt[1].data_ptr() if ada else None, frag_tidx.data_ptr() if ada else None, L if ada else 0,
+                     None if ada else nxt[1].data_ptr(), None if ada else nxt[2].data_ptr(), ln.data_ptr())
+            else:
+                self.gemm(a, lda, lin, h, C, M, EPI_NONE, residual=h, ldr=C)
+
         for li, lw in enumerate(w.layers):
             for which, (name, segs, nseg, mlen) in enumerate((("self_attn", (loc_start, loc_len), F, L),
                                                                ("global_attn", (glo_start, glo_len), n_obj, max_global))):
                 mod = w.mod[li * 2 + which]
-                call("pfpp_layernorm", h.data_ptr(), None, None, None, mod.data_ptr(), frag_tidx.data_ptr(), L, M, C, bf,
-                     ln.data_ptr(), None)
+                if not fuse or (li == 0 and which == 0):
+                    call("pfpp_layernorm", h.data_ptr(), None, None, None, mod.data_ptr(), frag_tidx.data_ptr(), L, M, C, bf,
+                         ln.data_ptr(), None)
                 self.gemm(ln, C, lw[name + ".qkv"], qkv, 3 * C, M)
                 if self.bf16 and which == 1 and D == 64 and self.tc_attention:
                     call("pfpp_attention_tc", qkv.data_ptr(), M, 3 * C, C, segs[0].data_ptr(), segs[1].data_ptr(), nseg,
@@ -440,11 +458,13 @@ class Engine:
                 else:
                     call("pfpp_attention_varlen", qkv.data_ptr(), 3 * C, 0, C, 2 * C, segs[0].data_ptr(),
                          segs[1].data_ptr(), nseg, mlen, H, D, bf, ao.data_ptr(), wm * C)
-                self.gemm(ao, C, lw[name + ".out"], h, C, M, EPI_NONE, residual=h, ldr=C)
-            call("pfpp_layernorm", h.data_ptr(), None, lw["norm3.w"].data_ptr(), lw["norm3.b"].data_ptr(), None, None, 0, M,
-                 C, bf, ln.data_ptr(), None)
+                res_proj(ao, C, lw[name + ".out"],
+                         ("mod", w.mod[li * 2 + 1]) if which == 0 else ("affine", lw["norm3.w"], lw["norm3.b"]))
+            if not fuse:
+                call("pfpp_layernorm", h.data_ptr(), None, lw["norm3.w"].data_ptr(), lw["norm3.b"].data_ptr(), None, None, 0,
+                     M, C, bf, ln.data_ptr(), None)
             self.gemm(ln, C, lw["ff1"], ff, 4 * C, M, EPI_GEGLU)
-            self.gemm(ff, 4 * C, lw["ff2"], h, C, M, EPI_NONE, residual=h, ldr=C)
+            res_proj(ff, 4 * C, lw["ff2"], ("mod", w.mod[(li + 1) * 2]) if li + 1 < n_layers else None)
             if trace is not None:
                 trace[f"layer{li}"] = h.clone()
         eps = self.buf("eps", (F, 8), torch.float32)

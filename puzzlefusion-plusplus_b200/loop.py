@@ -234,7 +234,7 @@ class StepContext:
     def get(e, slots, N, F, n_obj, max_global, n_enc=-1):
         # the launch sequence also depends on the engine's kernel-selection switches: part of the key, so that a
         # graph captured under other settings is never replayed
-        key = (slots, N, F, n_obj, max_global, e.T, e.fused_sa, e.tc_attention, e.local_tiles, e.coarse, n_enc)
+        key = (slots, N, F, n_obj, max_global, e.T, e.fused_sa, e.tc_attention, e.local_tiles, e.fused_ln, e.coarse, n_enc)
         cache = e._step_ctx
         ctx = cache.pop(key, None)
         if ctx is None:

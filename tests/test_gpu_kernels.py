@@ -293,6 +293,48 @@ def test_layernorm_variants(lib):
     assert torch.allclose(y.cpu(), ref, atol=5e-5)
 
 
+@pytest.mark.parametrize("M,K,kind", [(9675, 512, "ada"), (9675, 2048, "ada"), (300, 512, "affine"), (100, 2048, "mixed"),
+                                      (1000, 512, "mixed"), (129, 512, "ada")])
+def test_gemm_res_ln_matches_torch(lib, M, K, kind):
+    """pfpp_gemm_res_ln: h += A W^T + b (fp32) and the (Ada)LayerNorm of the new h as bf16, vs fp64 torch on the same
+    bf16 operands; rows that are not a multiple of the 256-row CTA pair, per-fragment timesteps inside one warp."""
+    C, L = 512, 25
+    g = torch.Generator().manual_seed(M + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(C, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(C, generator=g) * 0.1
+    h0 = torch.randn(M, C, generator=g) * 2 + 0.5
+    T = 7
+    mod = torch.randn(T, 2 * C, generator=g) * 0.3
+    n_grp = (M + L - 1) // L
+    if kind == "mixed":
+        grp = torch.randint(0, T, (n_grp,), generator=g, dtype=torch.int32)
+    else:
+        grp = torch.full((n_grp,), 3, dtype=torch.int32)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    da, dw, db, dh = a.to(DEV), w.to(DEV), bias.to(DEV), h0.to(DEV)
+    dmod, dgrp, dg, dbe = mod.to(DEV), grp.to(DEV), gamma.to(DEV), beta.to(DEV)
+    ln = torch.full((M, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ada = kind != "affine"
+    lib.call("pfpp_gemm_res_ln", da.data_ptr(), K, dw.data_ptr(), K, db.data_ptr(), dh.data_ptr(), M, K,
+             dmod.data_ptr() if ada else None, dgrp.data_ptr() if ada else None, L if ada else 0,
+             None if ada else dg.data_ptr(), None if ada else dbe.data_ptr(), ln.data_ptr())
+    torch.cuda.synchronize()
+    h_ref = h0.double() + a.double() @ w.double().T + bias.double()
+    assert torch.allclose(dh.cpu().double(), h_ref, atol=2e-5, rtol=1e-5), (dh.cpu().double() - h_ref).abs().max()
+    y = torch.nn.functional.layer_norm(dh.cpu().double(), (C,), None, None, 1e-5)
+    if ada:
+        m = mod[grp.long()].repeat_interleave(L, 0)[:M].double()
+        y = y * (1 + m[:, :C]) + m[:, C:]
+    else:
+        y = y * gamma.double() + beta.double()
+    out = ln.cpu().double()
+    assert torch.isfinite(out).all()
+    # bf16 rounding of the output: half an ulp = 2^-9 relative
+    err = (out - y).abs() / (y.abs() + 1e-2)
+    assert err.max() < 6e-3, err.max()
+
+
 @pytest.mark.parametrize("D,lens", [(64, [25, 25, 25]), (64, [500, 325, 50]), (32, [190, 36, 1])])
 def test_attention_varlen(lib, D, lens):
     H = 8
