@@ -186,6 +186,12 @@ int pfpp_attention_varlen(const void* qkv, int ld, int q_off, int k_off, int v_o
  * out is bf16 [M, C]. */
 int pfpp_attention_tc(const void* qkv, long long M, int ld, int C, const int* seg_start, const int* seg_len,
                       int n_segments, int max_len, int heads, int block, void* out, int ldo, cudaStream_t stream);
+/* The same block-diagonal local attention (attention.py:79 with self_mask) at its natural granularity: one warp per
+ * (block of `block` <= 32 consecutive tokens, head), warp-level mma.sync m16n8k16 + ldmatrix, no padding to 128-row tiles.
+ * Rows [i*block, (i+1)*block) of the packed [M, 3C] bf16 QKV matrix attend to each other; M % block == 0, head_dim 64.
+ * Same arithmetic as pfpp_attention_tc (bf16 operands, fp32 scores, bf16 probabilities, row sum of the rounded values). */
+int pfpp_attention_local(const void* qkv, long long M, int ld, int C, int heads, int block, void* out, int ldo,
+                         cudaStream_t stream);
 /* debug variant of pfpp_attention_tc: per-CTA clock stamps of the pipeline phases into trace[n_ctas][48] */
 int pfpp_attention_tc_trace(const void* qkv, long long M, int ld, int C, const int* seg_start, const int* seg_len,
                             int n_segments, int max_len, int heads, int block, void* out, int ldo, long long* trace,
@@ -299,7 +305,8 @@ typedef struct PfppDenoiserLayer {
 /* DenoiserTransformer (denoiser_transformer.py:13-202) + the scheduler's coefficient table */
 typedef struct PfppDenoiserWeights {
   int mode, C, heads, n_layers, P, L, latent_dim, T;
-  int tc_attention, local_tiles; /* mode 1: tcgen05 attention; 125-token tiles per local-attention CTA */
+  int tc_attention, local_tiles; /* mode 1: tcgen05 attention; local attention: 0 = one warp per fragment and head
+                                  * (pfpp_attention_local), n > 0 = tcgen05 with n 125-token tiles per CTA */
   int fused_ln; /* mode 1: out-proj / FF2 + residual + the following (Ada)LayerNorm as ONE kernel (pfpp_gemm_res_ln) */
   PfppLinear shape_embedding, param_fc;
   const float* ref_emb; /* [2, C] */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "pfpp_gemm_res_ln": [_P, _I, _P, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P],
     "pfpp_attention_varlen": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     "pfpp_attention_tc": [_P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P],
+    "pfpp_attention_local": [_P, _L, _I, _I, _I, _I, _P, _I, _P],
     "pfpp_attention_tc_trace": [_P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P],
     "pfpp_mean_pool": [_P, _I, _I, _I, _I, _P, _P],
     "pfpp_ddpm_step": [_P, _I, _P, _P, _P, _I, _P, _L, _P, _P, _I, _P, _P, _L, _P],

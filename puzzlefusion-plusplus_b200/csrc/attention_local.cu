@@ -1,0 +1,198 @@
+// Block-diagonal ("local") attention of the denoiser (attention.py:79 with self_mask, denoiser_transformer.py:168-171):
+// every fragment's 25 latent tokens attend to each other only.  One WARP = one (block of <= 32 tokens, head):
+//
+//   Q, K, V  [blk x 64] bf16     cp.async (16-byte chunks) into three private 4 KB shared-memory tiles, XOR-swizzled
+//   S = Q K^T, O = P V           warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate), operands via ldmatrix
+//   softmax                      in the accumulator fragments (quad shuffles), P re-used as the A operand in registers
+//
+// The tcgen05 path (attention_ws.cu) needs 128-row tiles, so a 25 x 25 block costs a 128 x 64 score panel and a
+// 128 x 64 x 64 PV product: >= 80 % of its tensor and MUFU work is masked away and the kernel ends up bound by its
+// compulsory QKV read at a fifth of the HBM rate.  At this granularity the legacy warp-level MMA is the right tool:
+// no padding beyond 32 x 32, no TMEM / mbarrier round trips, 16 independent warps per SM hide the load latency.
+// Arithmetic is the same as the tcgen05 kernel's: bf16 operands, fp32 scores, exp2 with the row maximum, probabilities
+// rounded to bf16 for the PV product, the row sum taken over the ROUNDED probabilities, fp32 output scaled by 1 / sum.
+// A block's result does not depend on its neighbours (batch == the same objects one by one, bit for bit).
+#include "common.cuh"
+#include "../../include/pfpp.h"
+
+namespace {
+
+constexpr int AL_D = 64;            // head dimension
+constexpr int AL_ROWS = 32;         // padded block
+constexpr int AL_TILE = AL_ROWS * AL_D * 2;  // 4 KB
+constexpr int AL_WARPS = 8;
+
+__device__ __forceinline__ uint32_t al_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float al_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// byte offset of 16-byte chunk c of row r inside a [32 x 128 B] tile
+__device__ __forceinline__ uint32_t al_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+__global__ void __launch_bounds__(32 * AL_WARPS, 2)
+    attention_local_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int C, long long n_tasks, int heads, int blk,
+                           float scale_log2e, __nv_bfloat16* __restrict__ out, int ldo) {
+  extern __shared__ __align__(1024) uint8_t al_smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* tq = al_smem_raw + warp * 3 * AL_TILE;
+  uint8_t *tk = tq + AL_TILE, *tv = tk + AL_TILE;
+  const uint32_t sq = al_smem(tq), sk = al_smem(tk), sv = al_smem(tv);
+  // rows blk..31 are never written by the copies: zero them once (masked keys must meet finite V rows: 0 * NaN = NaN)
+  for (int i = lane; i < (AL_ROWS - blk) * 8 * 3; i += 32) {
+    const int m = i / ((AL_ROWS - blk) * 8), rc = i - m * (AL_ROWS - blk) * 8;
+    *reinterpret_cast<uint4*>(tq + m * AL_TILE + al_off(blk + rc / 8, rc & 7)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  const int g = lane >> 2, t = lane & 3;
+  const int mi = lane >> 3, ri = lane & 7;  // ldmatrix: this lane addresses row ri of 8x8 matrix mi
+  const int n_mt = blk > 16 ? 2 : 1;
+  for (long long task = (long long)blockIdx.x * AL_WARPS + warp; task < n_tasks; task += (long long)gridDim.x * AL_WARPS) {
+    const long long b = task / heads;
+    const int h = (int)(task - b * heads);
+    const long long row0 = b * blk;
+    __syncwarp();  // the previous task's reads of the tiles are complete
+    for (int i = lane; i < blk * 8 * 3; i += 32) {
+      const int m = i / (blk * 8), rc = i - m * blk * 8, r = rc >> 3, c = rc & 7;
+      const __nv_bfloat16* src = qkv + (size_t)(row0 + r) * ld + m * C + h * AL_D + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sq + m * AL_TILE + al_off(r, c)), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    uint32_t ostage[2][8][2];  // bf16x2 output pairs: [m-tile][d-tile][row half]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      if (mt < n_mt) {
+        // ---- S = Q K^T : 16 query rows x 32 keys
+        float s[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t a0, a1, a2, a3;
+          ldsm_x4(sq + al_off(mt * 16 + (mi & 1) * 8 + ri, ks * 2 + (mi >> 1)), a0, a1, a2, a3);
+#pragma unroll
+          for (int np = 0; np < 2; ++np) {  // key tiles 2 np, 2 np + 1
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(sk + al_off(np * 16 + (mi >> 1) * 8 + ri, ks * 2 + (mi & 1)), b0, b1, b2, b3);
+            mma_bf16(s[2 * np], a0, a1, a2, a3, b0, b1);
+            mma_bf16(s[2 * np + 1], a0, a1, a2, a3, b2, b3);
+          }
+        }
+        // ---- softmax over the blk valid keys; rows g (regs 0, 1) and g + 8 (regs 2, 3)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (nt * 8 + 2 * t + e >= blk) s[nt][e] = s[nt][2 + e] = -INFINITY;
+            mx0 = fmaxf(mx0, s[nt][e]);
+            mx1 = fmaxf(mx1, s[nt][2 + e]);
+          }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float nm0 = -mx0 * scale_log2e, nm1 = -mx1 * scale_log2e;
+        uint32_t p[4][2];
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          __nv_bfloat162 q0 = __floats2bfloat162_rn(al_ex2(fmaf(s[nt][0], scale_log2e, nm0)), al_ex2(fmaf(s[nt][1], scale_log2e, nm0)));
+          __nv_bfloat162 q1 = __floats2bfloat162_rn(al_ex2(fmaf(s[nt][2], scale_log2e, nm1)), al_ex2(fmaf(s[nt][3], scale_log2e, nm1)));
+          l0 += __low2float(q0) + __high2float(q0);
+          l1 += __low2float(q1) + __high2float(q1);
+          p[nt][0] = *reinterpret_cast<uint32_t*>(&q0);
+          p[nt][1] = *reinterpret_cast<uint32_t*>(&q1);
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        // ---- O = P V : 16 rows x 64 dims, keys in two k16 steps
+        float o[8][4];
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {  // dim tiles 2 dp, 2 dp + 1
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(sv + al_off(kk * 16 + (mi & 1) * 8 + ri, 2 * dp + (mi >> 1)), b0, b1, b2, b3);
+            mma_bf16(o[2 * dp], p[2 * kk][0], p[2 * kk][1], p[2 * kk + 1][0], p[2 * kk + 1][1], b0, b1);
+            mma_bf16(o[2 * dp + 1], p[2 * kk][0], p[2 * kk][1], p[2 * kk + 1][0], p[2 * kk + 1][1], b2, b3);
+          }
+        }
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+          __nv_bfloat162 r0 = __floats2bfloat162_rn(o[dt][0] * i0, o[dt][1] * i0);
+          __nv_bfloat162 r1 = __floats2bfloat162_rn(o[dt][2] * i1, o[dt][3] * i1);
+          ostage[mt][dt][0] = *reinterpret_cast<uint32_t*>(&r0);
+          ostage[mt][dt][1] = *reinterpret_cast<uint32_t*>(&r1);
+        }
+      }
+    }
+    // ---- output: fragments -> the Q tile (every lane is done with Q) -> 16-byte coalesced stores of rows < blk
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      if (mt < n_mt) {
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+          *reinterpret_cast<uint32_t*>(tq + al_off(mt * 16 + g, dt) + t * 4) = ostage[mt][dt][0];
+          *reinterpret_cast<uint32_t*>(tq + al_off(mt * 16 + 8 + g, dt) + t * 4) = ostage[mt][dt][1];
+        }
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < blk * 8; i += 32) {
+      const int r = i >> 3, c = i & 7;
+      *reinterpret_cast<uint4*>(out + (size_t)(row0 + r) * ldo + h * AL_D + c * 8) = *reinterpret_cast<const uint4*>(tq + al_off(r, c));
+    }
+    // rows >= blk of the Q tile were overwritten by the staging: restore the zeros for the next task
+    if (n_mt * 16 > blk) {
+      __syncwarp();
+      for (int i = lane; i < (n_mt * 16 - blk) * 8; i += 32) *reinterpret_cast<uint4*>(tq + al_off(blk + (i >> 3), i & 7)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int pfpp_attention_local(const void* qkv, long long M, int ld, int C, int heads, int block, void* out, int ldo,
+                                    cudaStream_t stream) {
+  PFPP_CHECK_ARG(qkv && out && heads > 0 && C == heads * AL_D && block > 0 && block <= AL_ROWS && M >= 0 && (M % block) == 0);
+  PFPP_CHECK_ARG((ld % 8) == 0 && (ldo % 8) == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0);
+  if (M == 0) return PFPP_OK;
+  const long long n_tasks = M / block * heads;
+  const int smem = AL_WARPS * 3 * AL_TILE;
+  PFPP_ENSURE_SMEM(attention_local_kernel, smem);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  long long grid = (n_tasks + AL_WARPS - 1) / AL_WARPS;
+  if (grid > 2LL * sms) grid = 2LL * sms;
+  const float scale_log2e = 1.4426950408889634f / sqrtf((float)AL_D);
+  attention_local_kernel<<<(unsigned)grid, 32 * AL_WARPS, smem, stream>>>((const __nv_bfloat16*)qkv, ld, C, n_tasks, heads, block,
+                                                                          scale_log2e, (__nv_bfloat16*)out, ldo);
+  PFPP_RETURN_LAST();
+}

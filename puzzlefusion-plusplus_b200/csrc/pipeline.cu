@@ -208,7 +208,7 @@ DenBufs plan_denoiser(Bump& b, const PfppDenoiserWeights* w, int F) {
   d.h0 = b.take<float>((size_t)F * 2 * C);
   d.ht = b.take<float>((size_t)F * (C / 2));
   d.hr = b.take<float>((size_t)F * (C / 2));
-  const int per = 5 * w->local_tiles;
+  const int per = 5 * (w->local_tiles > 0 ? w->local_tiles : 1);
   d.n_loc = (F + per - 1) / per;
   d.loc_start = b.take<int>(d.n_loc);
   d.loc_len = b.take<int>(d.n_loc);
@@ -227,7 +227,8 @@ int run_denoiser(const PfppDenoiserWeights* w, const float* x, const float* scal
   PF(gemm(mode, d.feat_tok, d.ld_tok, w->shape_embedding, d.shape_emb, C, M, PFPP_EPI_NONE, nullptr, 0, false, s));
   PF(gemm(mode, d.feat_par, d.ld_par, w->param_fc, d.x_emb, C, F, PFPP_EPI_NONE, nullptr, 0, false, s));
   PF(pfpp_combine_embed(d.shape_emb, d.x_emb, w->ref_emb, w->pe, frag_slot, ref, F, w->P, L, C, d.h, s));
-  const bool tc_local = mode == 1 && D == 64 && w->tc_attention && 5 * L <= 128;
+  const bool mma_local = mode == 1 && D == 64 && w->tc_attention && w->local_tiles == 0 && L <= 32;
+  const bool tc_local = !mma_local && mode == 1 && D == 64 && w->tc_attention && 5 * L <= 128;
   const bool tc_global = mode == 1 && D == 64 && w->tc_attention;
   if (tc_local) {
     local_segments_kernel<<<pfpp_cdiv(d.n_loc, 128), 128, 0, s>>>(d.n_loc, 5 * w->local_tiles * L, M, d.loc_start, d.loc_len);
@@ -244,6 +245,9 @@ int run_denoiser(const PfppDenoiserWeights* w, const float* x, const float* scal
       PF(gemm(mode, d.ln, C, lw.qkv[which], d.qkv, 3 * C, M, PFPP_EPI_NONE, nullptr, 0, mode != 2, s));
       if (which == 1 && tc_global) {
         PF(pfpp_attention_tc(d.qkv, M, 3 * C, C, obj_seg_start, obj_seg_len, n_obj, max_global, H, 0, d.ao, C, s));
+      } else if (which == 0 && mma_local) {
+        // block-diagonal local attention: one warp per (fragment, head)
+        PF(pfpp_attention_local(d.qkv, M, 3 * C, C, H, L, d.ao, C, s));
       } else if (which == 0 && tc_local) {
         // block-diagonal local attention: 5 fragments (125 tokens) per 128-row tensor-core tile
         PF(pfpp_attention_tc(d.qkv, M, 3 * C, C, d.loc_start, d.loc_len, d.n_loc, 5 * L * w->local_tiles, H, L, d.ao, C, s));

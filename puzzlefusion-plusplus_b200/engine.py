@@ -77,7 +77,9 @@ class Engine:
         self.C = self.den.C
         self.tc_attention = True  # tcgen05 attention in bf16 mode (segments > 512 tokens stream K/V through a ring)
         self.fused_sa = True     # fused gather + 3-layer MLP + max tcgen05 kernel in bf16 mode
-        self.local_tiles = 4     # 125-token tiles (5 fragments) per local-attention CTA, two per softmax group
+        # local attention in bf16 mode: 0 = one warp per (fragment, head) on warp-level MMAs (pfpp_attention_local),
+        # n > 0 = the tcgen05 kernel with n 125-token tiles (5 fragments each) per CTA
+        self.local_tiles = 0
         self.fused_ln = True     # bf16 mode: out-proj / FF2 + residual + next (Ada)LayerNorm in one kernel
         self.coarse = True       # run the stages through the coarse C entry points (pfpp_encoder_forward, ...)
         # Reference parts keep their pose for a whole outer iteration (clamped every step, auto_aggl.py:150), so their
@@ -450,6 +452,8 @@ class Engine:
                 if self.bf16 and which == 1 and D == 64 and self.tc_attention:
                     call("pfpp_attention_tc", qkv.data_ptr(), M, 3 * C, C, segs[0].data_ptr(), segs[1].data_ptr(), nseg,
                          mlen, H, 0, ao.data_ptr(), C)
+                elif self.bf16 and which == 0 and D == 64 and self.tc_attention and self.local_tiles == 0 and L <= 32:
+                    call("pfpp_attention_local", qkv.data_ptr(), M, 3 * C, C, H, L, ao.data_ptr(), C)
                 elif self.bf16 and which == 0 and D == 64 and self.tc_attention and 5 * L <= 128:
                     # block-diagonal local attention: 5 fragments (125 tokens) per 128-row tensor-core tile
                     ts, tl = self._local_tc_segments(F)

@@ -514,3 +514,32 @@ def test_attention_tcgen05_block_diagonal(lib, F, tiles):
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(F, L, C)
     assert (o - ref).abs().max() <= 2e-2, (o - ref).abs().max()
 
+
+
+@pytest.mark.parametrize("F,L,qscale", [(1, 25, 1.0), (13, 25, 4.0), (640, 25, 1.0), (7, 32, 1.0), (9, 16, 2.0), (5, 7, 1.0)])
+def test_attention_local_warp_mma(lib, F, L, qscale):
+    """pfpp_attention_local: one warp per (block of L tokens, head) vs per-block torch SDPA; the result of a block does
+    not depend on where it sits in the batch (bit for bit)."""
+    H, D = 8, 64
+    C = H * D
+    M = F * L
+    g = torch.Generator().manual_seed(F * 100 + L)
+    qkv = torch.randn(M, 3 * C, generator=g)
+    qkv[:, :C] *= qscale
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.full((M, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    dq = qkv.to(DEV)
+    lib.call("pfpp_attention_local", dq.data_ptr(), M, 3 * C, C, H, L, out.data_ptr(), C)
+    torch.cuda.synchronize()
+    o = out.cpu().float().view(F, L, C)
+    assert torch.isfinite(o).all()
+    q, k, v = [t.reshape(F, L, H, D).transpose(1, 2) for t in qkv.float().chunk(3, -1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(F, L, C)
+    assert (o - ref).abs().max() <= 2e-2, (o - ref).abs().max()
+    if F > 1:
+        # the last block alone
+        one = torch.zeros(L, C, device=DEV, dtype=torch.bfloat16)
+        last = dq[-L:].contiguous()
+        lib.call("pfpp_attention_local", last.data_ptr(), L, 3 * C, C, H, L, one.data_ptr(), C)
+        torch.cuda.synchronize()
+        assert torch.equal(one.cpu(), out[-L:].cpu())

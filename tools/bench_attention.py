@@ -55,6 +55,9 @@ for entry in ("pfpp_attention_tc",):
         timeit(f"{entry} local x{tiles}", lambda: _lib.call(entry, qkv.data_ptr(), M, 3 * C, C, st.data_ptr(), ln.data_ptr(), n,
                                                            125 * tiles, H, L, out.data_ptr(), C), l_flops)
 
+timeit("pfpp_attention_local (warp MMA)", lambda: _lib.call("pfpp_attention_local", qkv.data_ptr(), M, 3 * C, C, H, L,
+                                                            out.data_ptr(), C), l_flops)
+
 if "--trace" in sys.argv:
     names = {1: "setup done", 2: "TMA issued", 3: "first S issued", 10: "softmax group 0 done", 11: "CTA end"}
     for label, per, blk in (("global", 500, 0), ("local x2", 250, L), ("local x4", 500, L)):
