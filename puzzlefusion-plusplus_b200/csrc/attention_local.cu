@@ -60,15 +60,35 @@ __global__ void __launch_bounds__(32 * AL_WARPS, 2)
   const int g = lane >> 2, t = lane & 3;
   const int mi = lane >> 3, ri = lane & 7;  // ldmatrix: this lane addresses row ri of 8x8 matrix mi
   const int n_mt = blk > 16 ? 2 : 1;
-  for (long long task = (long long)blockIdx.x * AL_WARPS + warp; task < n_tasks; task += (long long)gridDim.x * AL_WARPS) {
-    const long long b = task / heads;
-    const int h = (int)(task - b * heads);
-    const long long row0 = b * blk;
+  // Every shared-memory address below is (lane constant) + (compile-time constant): the XOR swizzle of chunk 2k + b on a
+  // row with (row & 7) == ri is ((2k) ^ (b ^ ri)) << 4, so four chunk offsets per operand cover the k / dim steps.
+  uint32_t aq[4], ak[4], av[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t xq = (uint32_t)(((2 * k) ^ ((mi >> 1) ^ ri)) << 4), xk = (uint32_t)(((2 * k) ^ ((mi & 1) ^ ri)) << 4);
+    aq[k] = sq + ((mi & 1) * 8 + ri) * 128 + xq;   // Q: rows (mi & 1) * 8 + ri, chunk 2 k + (mi >> 1)
+    ak[k] = sk + ((mi >> 1) * 8 + ri) * 128 + xk;  // K: rows (mi >> 1) * 8 + ri, chunk 2 k + (mi & 1)
+    av[k] = sv + ((mi & 1) * 8 + ri) * 128 + xq;   // V: rows (mi & 1) * 8 + ri, chunk 2 k + (mi >> 1)
+  }
+  // copies: lane -> 16-byte chunk cc of rows r0 + 4 j; (row & 7) is r0 for even j and r0 ^ 4 for odd j
+  const int r0 = lane >> 3, cc = lane & 7;
+  const uint32_t cp_even = (uint32_t)(r0 * 128 + ((cc ^ r0) << 4)), cp_odd = (uint32_t)(r0 * 128 + ((cc ^ r0 ^ 4) << 4));
+  const int n_tasks32 = (int)n_tasks;
+  for (int task = blockIdx.x * AL_WARPS + warp; task < n_tasks32; task += gridDim.x * AL_WARPS) {
+    const int b = task / heads;
+    const int h = task - b * heads;
+    const long long row0 = (long long)b * blk;
     __syncwarp();  // the previous task's reads of the tiles are complete
-    for (int i = lane; i < blk * 8 * 3; i += 32) {
-      const int m = i / (blk * 8), rc = i - m * blk * 8, r = rc >> 3, c = rc & 7;
-      const __nv_bfloat16* src = qkv + (size_t)(row0 + r) * ld + m * C + h * AL_D + c * 8;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sq + m * AL_TILE + al_off(r, c)), "l"(src) : "memory");
+    const __nv_bfloat16* src0 = qkv + (size_t)(row0 + r0) * ld + h * AL_D + cc * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (r0 + 4 * j < blk) {
+        const __nv_bfloat16* src = src0 + (size_t)(4 * j) * ld;
+        const uint32_t dst = sq + j * 512 + ((j & 1) ? cp_odd : cp_even);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + AL_TILE), "l"(src + C) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2 * AL_TILE), "l"(src + 2 * C) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -84,11 +104,11 @@ __global__ void __launch_bounds__(32 * AL_WARPS, 2)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           uint32_t a0, a1, a2, a3;
-          ldsm_x4(sq + al_off(mt * 16 + (mi & 1) * 8 + ri, ks * 2 + (mi >> 1)), a0, a1, a2, a3);
+          ldsm_x4(aq[ks] + mt * 2048, a0, a1, a2, a3);
 #pragma unroll
           for (int np = 0; np < 2; ++np) {  // key tiles 2 np, 2 np + 1
             uint32_t b0, b1, b2, b3;
-            ldsm_x4(sk + al_off(np * 16 + (mi >> 1) * 8 + ri, ks * 2 + (mi & 1)), b0, b1, b2, b3);
+            ldsm_x4(ak[ks] + np * 2048, b0, b1, b2, b3);
             mma_bf16(s[2 * np], a0, a1, a2, a3, b0, b1);
             mma_bf16(s[2 * np + 1], a0, a1, a2, a3, b2, b3);
           }
@@ -133,7 +153,7 @@ __global__ void __launch_bounds__(32 * AL_WARPS, 2)
 #pragma unroll
           for (int dp = 0; dp < 4; ++dp) {  // dim tiles 2 dp, 2 dp + 1
             uint32_t b0, b1, b2, b3;
-            ldsm_x4_t(sv + al_off(kk * 16 + (mi & 1) * 8 + ri, 2 * dp + (mi >> 1)), b0, b1, b2, b3);
+            ldsm_x4_t(av[dp] + kk * 2048, b0, b1, b2, b3);
             mma_bf16(o[2 * dp], p[2 * kk][0], p[2 * kk][1], p[2 * kk + 1][0], p[2 * kk + 1][1], b0, b1);
             mma_bf16(o[2 * dp + 1], p[2 * kk][0], p[2 * kk][1], p[2 * kk + 1][0], p[2 * kk + 1][1], b2, b3);
           }
@@ -161,15 +181,13 @@ __global__ void __launch_bounds__(32 * AL_WARPS, 2)
       }
     }
     __syncwarp();
-    for (int i = lane; i < blk * 8; i += 32) {
-      const int r = i >> 3, c = i & 7;
-      *reinterpret_cast<uint4*>(out + (size_t)(row0 + r) * ldo + h * AL_D + c * 8) = *reinterpret_cast<const uint4*>(tq + al_off(r, c));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (r0 + 4 * j < blk)
+        *reinterpret_cast<uint4*>(out + (size_t)(row0 + r0 + 4 * j) * ldo + h * AL_D + cc * 8) =
+            *reinterpret_cast<const uint4*>(tq + j * 512 + ((j & 1) ? cp_odd : cp_even));
     }
-    // rows >= blk of the Q tile were overwritten by the staging: restore the zeros for the next task
-    if (n_mt * 16 > blk) {
-      __syncwarp();
-      for (int i = lane; i < (n_mt * 16 - blk) * 8; i += 32) *reinterpret_cast<uint4*>(tq + al_off(blk + (i >> 3), i & 7)) = make_uint4(0u, 0u, 0u, 0u);
-    }
+    // rows >= blk of the Q tile now hold finite leftovers of the staging: they only ever feed the discarded query rows
   }
 }
 
