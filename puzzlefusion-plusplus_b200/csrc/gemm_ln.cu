@@ -17,10 +17,11 @@
 //   warp 0      TMA producer (both CTAs; all loads signal the leader's `full` barrier), 3-stage ring
 //   warp 1      MMA issuer (leader CTA only): per k16 step two M 256 x N 256 instructions (the two column halves)
 //   warps 2-9   epilogue: warp -> TMEM lane quarter (warp % 4) and column half ((warp - 2) / 4); thread = row.
-//               pass 1, per 32-column chunk: accumulator + bias + residual (coalesced global read, prefetched one
-//               chunk ahead, transposed through a private swizzled 4 KB tile) -> shifted row sums -> value parked
-//               back in TMEM -> coalesced fp32 store of h; (mean, M2) of the two column halves combined (Chan)
-//               through shared memory;
+//               pass 1, per 32-column chunk: the residual tile [32 rows x 32 cols] arrives by TMA (128B-swizzled, a
+//               ring of 5 tiles per warp: two filled under the main loop, three in the drained operand ring);
+//               accumulator + bias + residual -> shifted row sums -> value parked back in TMEM and written over the
+//               residual in its tile -> TMA store of h; (mean, M2) of the two column halves combined (Chan) through
+//               shared memory;
 //               pass 2, per 64-column slab: normalise + modulate -> bf16 -> swizzled box -> TMA store.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -35,11 +36,15 @@ constexpr int GL_C = 512;                               // row width (d_model)
 constexpr int GL_BM = 128, GL_BK = 64, GL_STAGES = 3;
 constexpr uint32_t GL_BOX_BYTES = 128 * GL_BK * 2;      // one [128 x 64] bf16 box = 16 KB
 constexpr uint32_t GL_STAGE_BYTES = 3 * GL_BOX_BYTES;   // A rows + two W shares
-constexpr uint32_t GL_OFF_EPI = GL_STAGES * GL_STAGE_BYTES;          // 8 warps x 4 KB transpose tiles
-constexpr uint32_t GL_OFF_STAT = GL_OFF_EPI + 8 * 4096;              // [2 halves][128 rows] (mean, M2)
+// residual tiles [32 rows x 32 fp32] (4 KB, SWIZZLE_128B) of the epilogue warps: per warp a ring of GL_RT tiles, the first
+// two in a dedicated area (filled while the main loop runs), the others in the operand ring once the MMAs are done
+constexpr int GL_RT = 5;
+constexpr uint32_t GL_OFF_EPI = GL_STAGES * GL_STAGE_BYTES;          // 8 warps x 2 tiles
+constexpr uint32_t GL_OFF_STAT = GL_OFF_EPI + 8 * 2 * 4096;          // [2 halves][128 rows] (mean, M2)
 constexpr uint32_t GL_OFF_TAB = GL_OFF_STAT + 2 * 128 * 8;           // bias | multiplier | offset, 512 floats each
-constexpr uint32_t GL_OFF_BAR = GL_OFF_TAB + 3 * GL_C * 4;
-constexpr uint32_t GL_SMEM_BYTES = GL_OFF_BAR + 128 + 1024;
+constexpr uint32_t GL_OFF_BAR = GL_OFF_TAB + 3 * GL_C * 4;           // full[3] empty[3] acc | tmem slot | res[8][GL_RT]
+constexpr uint32_t GL_SMEM_BYTES = GL_OFF_BAR + 512 + 1024;
+static_assert(8 * (GL_RT - 2) * 4096 <= GL_STAGES * GL_STAGE_BYTES, "late residual tiles live in the operand ring");
 constexpr int GL_THREADS = 64 + 256;
 // D = f32, A = B = bf16, both K-major, M = 256 (128 per CTA), N = 256
 constexpr uint32_t GL_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -57,12 +62,14 @@ struct LnParams {
 
 __global__ void __launch_bounds__(GL_THREADS, 1)
     gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                       const __grid_constant__ CUtensorMap map_o, const LnParams p) {
+                       const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_h,
+                       const LnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar_full = base + GL_OFF_BAR, bar_empty = bar_full + 8 * GL_STAGES, bar_acc = bar_empty + 8 * GL_STAGES;
   const uint32_t tmem_slot = bar_acc + 8;
+  const uint32_t bar_res = tmem_slot + 8;  // [8 warps][GL_RT]: a residual tile has landed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
@@ -75,6 +82,7 @@ __global__ void __launch_bounds__(GL_THREADS, 1)
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
+    for (int i = 0; i < 8 * GL_RT; ++i) mbar_init(bar_res + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -126,10 +134,27 @@ __global__ void __launch_bounds__(GL_THREADS, 1)
     const int row = m0 + q * 32 + lane;                       // this thread's row
     const int col0 = ch * 256;                                // this warp's column half
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + col0;
-    uint4* stage = reinterpret_cast<uint4*>(bp + GL_OFF_EPI + (warp - 2) * 4096);
-    const uint32_t stage_addr = base + GL_OFF_EPI + (warp - 2) * 4096;
-    const int rr = lane >> 3, cg = lane & 7;                  // coalesced layout: rows rr + 4 i, 16-byte column group cg
+    const int ew = warp - 2;                                  // epilogue warp 0..7
+    // residual tile t of this warp: t < 2 dedicated, t >= 2 in the (by then idle) operand ring
+    auto tile_off = [&](int t) -> uint32_t {
+      return t < 2 ? GL_OFF_EPI + (uint32_t)(ew * 2 + t) * 4096u : (uint32_t)(ew * (GL_RT - 2) + (t - 2)) * 4096u;
+    };
+    const uint32_t my_res = bar_res + 8 * (ew * GL_RT);
+    uint4* stage = reinterpret_cast<uint4*>(bp + tile_off(0));  // pass 2 re-uses tile 0 as its bf16 output box
+    const uint32_t stage_addr = base + tile_off(0);
     float* tab = reinterpret_cast<float*>(bp + GL_OFF_TAB);   // [0,512) bias, [512,1024) multiplier, [1024,1536) offset
+    // the residual h[32 rows x 32 cols] of chunk c arrives by TMA, 128B-swizzled: the thread that owns a row reads it
+    // with conflict-free 16-byte loads, overwrites it in place with the new h and the TMA engine stores the tile back --
+    // no transposes through the LSU, no global loads / stores issued by the SM
+    auto fetch = [&](int c) {  // lane 0
+      const int t = c % GL_RT;
+      mbar_expect_tx(my_res + 8 * t, 4096);
+      tma_load_2d(base + tile_off(t), &map_h, my_res + 8 * t, col0 + c * 32, m0 + q * 32);
+    };
+    if (lane == 0) {
+      fetch(0);
+      fetch(1);
+    }
     // tables of the CTA's first row's modulation group (the DDPM step: every row of the batch shares one timestep)
     const float* mrow0 = nullptr;
     if (p.mod) mrow0 = p.mod + (size_t)p.row_group[(m0 < p.M ? m0 : p.M - 1) / p.rows_per_group] * 2 * GL_C;
@@ -138,47 +163,34 @@ __global__ void __launch_bounds__(GL_THREADS, 1)
       tab[GL_C + i] = p.mod ? 1.0f + mrow0[i] : p.gamma[i];
       tab[2 * GL_C + i] = p.mod ? mrow0[GL_C + i] : p.beta[i];
     }
-    // residual block [32 rows x 32 cols] of h: coalesced 128-byte row segments; chunk 0 is fetched under the main loop
-    float4 res[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = m0 + q * 32 + rr + 4 * i;
-      res[i] = r < p.M ? *reinterpret_cast<const float4*>(p.h + (size_t)r * GL_C + col0 + 4 * cg) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     asm volatile("bar.sync 5, 256;" ::: "memory");            // tables written
     mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (lane == 0) {  // every MMA has completed: the operand ring is free
+#pragma unroll
+      for (int c = 2; c < GL_RT; ++c) fetch(c);
+    }
     // ---- pass 1: h_new = acc + bias + h ; shifted row sums (shift = the row's first value of this half)
     float x0 = 0.f, sd = 0.f, sq = 0.f;
 #pragma unroll 1
     for (int c = 0; c < 8; ++c) {
       const int n0 = col0 + c * 32;
+      const int t = c % GL_RT;
       uint32_t v[32];
       tmem_ld32(taddr + c * 32, v);
+      uint4* tile = reinterpret_cast<uint4*>(bp + tile_off(t)) + lane * 8;  // this thread's row
+      mbar_wait(my_res + 8 * t, (c / GL_RT) & 1);
+      uint4 r4[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rr + 4 * i;
-        stage[r * 8 + (cg ^ (r & 7))] = make_uint4(__float_as_uint(res[i].x), __float_as_uint(res[i].y), __float_as_uint(res[i].z),
-                                                   __float_as_uint(res[i].w));
-      }
-      if (c + 1 < 8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = m0 + q * 32 + rr + 4 * i;
-          res[i] = r < p.M ? *reinterpret_cast<const float4*>(p.h + (size_t)r * GL_C + n0 + 32 + 4 * cg)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
+      for (int j = 0; j < 8; ++j) r4[j] = tile[j ^ (lane & 7)];
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint4 t = stage[lane * 8 + (j ^ (lane & 7))];
         const float4 b4 = *reinterpret_cast<const float4*>(tab + n0 + 4 * j);
-        v[4 * j] = __float_as_uint((__uint_as_float(v[4 * j]) + b4.x) + __uint_as_float(t.x));
-        v[4 * j + 1] = __float_as_uint((__uint_as_float(v[4 * j + 1]) + b4.y) + __uint_as_float(t.y));
-        v[4 * j + 2] = __float_as_uint((__uint_as_float(v[4 * j + 2]) + b4.z) + __uint_as_float(t.z));
-        v[4 * j + 3] = __float_as_uint((__uint_as_float(v[4 * j + 3]) + b4.w) + __uint_as_float(t.w));
+        v[4 * j] = __float_as_uint((__uint_as_float(v[4 * j]) + b4.x) + __uint_as_float(r4[j].x));
+        v[4 * j + 1] = __float_as_uint((__uint_as_float(v[4 * j + 1]) + b4.y) + __uint_as_float(r4[j].y));
+        v[4 * j + 2] = __float_as_uint((__uint_as_float(v[4 * j + 2]) + b4.z) + __uint_as_float(r4[j].z));
+        v[4 * j + 3] = __float_as_uint((__uint_as_float(v[4 * j + 3]) + b4.w) + __uint_as_float(r4[j].w));
       }
       if (c == 0) x0 = __uint_as_float(v[0]);
 #pragma unroll
@@ -188,18 +200,19 @@ __global__ void __launch_bounds__(GL_THREADS, 1)
         sq += d * d;
       }
       tmem_st32(taddr + c * 32, v);  // parked for pass 2
-      __syncwarp();                  // every lane has read its row of the residual tile
 #pragma unroll
-      for (int j = 0; j < 8; ++j) stage[lane * 8 + (j ^ (lane & 7))] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 8; ++j) tile[j ^ (lane & 7)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rr + 4 * i;
-        const int grow = m0 + q * 32 + r;
-        const uint4 t = stage[r * 8 + (cg ^ (r & 7))];
-        if (grow < p.M) *reinterpret_cast<uint4*>(p.h + (size_t)grow * GL_C + n0 + 4 * cg) = t;
+      if (lane == 0) {
+        if (m0 + q * 32 < p.M) tma_store_2d(&map_h, base + tile_off(t), n0, m0 + q * 32);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (c >= 2 && c + GL_RT - 2 < 8) {
+          // the store of chunk c - 2 has finished reading its tile: refill it with the residual of chunk c + GL_RT - 2
+          asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          fetch(c + GL_RT - 2);
+        }
       }
-      __syncwarp();
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     // ---- row statistics: this half's (mean, M2) -> shared memory -> combined with the other half (Chan et al.)
@@ -308,13 +321,23 @@ extern "C" int pfpp_gemm_res_ln(const void* A, int lda, const void* W, int ldw, 
                  (((uintptr_t)h) & 15) == 0);
   PFPP_CHECK_ARG(mod ? (row_group && rows_per_group > 0) : (gamma && beta));
   if (M == 0) return PFPP_OK;
-  CUtensorMap ma, mw, mo;
+  CUtensorMap ma, mw, mo, mh;
   int rc = gl_map(&ma, A, M, K, lda, GL_BM);
   if (rc) return rc;
   rc = gl_map(&mw, W, GL_C, K, ldw, 128);
   if (rc) return rc;
   rc = gl_map(&mo, ln_out, M, GL_C, GL_C, 32);
   if (rc) return rc;
+  {  // the residual stream as [32 x 32] fp32 boxes (128-byte rows, 128B swizzle)
+    auto fn = gl_encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)GL_C, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)GL_C * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    if (fn(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return PFPP_EINVAL;
+  }
   LnParams p{bias, h, mod, row_group, rows_per_group, gamma, beta, M, K};
   PFPP_ENSURE_SMEM(gemm_res_ln_kernel, GL_SMEM_BYTES);
   cudaLaunchConfig_t cfg{};
@@ -329,7 +352,7 @@ extern "C" int pfpp_gemm_res_ln(const void* A, int lda, const void* W, int ldw, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_res_ln_kernel, ma, mw, mo, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_res_ln_kernel, ma, mw, mo, mh, p);
   if (e != cudaSuccess) return (int)e;
   PFPP_RETURN_LAST();
 }
