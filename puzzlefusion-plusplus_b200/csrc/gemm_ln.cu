@@ -193,11 +193,16 @@ __global__ void __launch_bounds__(GL_THREADS, 1)
         v[4 * j + 3] = __float_as_uint((__uint_as_float(v[4 * j + 3]) + b4.w) + __uint_as_float(r4[j].w));
       }
       if (c == 0) x0 = __uint_as_float(v[0]);
+      {  // four independent chains per sum (a single one is 32 dependent adds per chunk)
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float d = __uint_as_float(v[j]) - x0;
-        sd += d;
-        sq += d * d;
+        for (int j = 0; j < 32; ++j) {
+          const float d = __uint_as_float(v[j]) - x0;
+          s4[j & 3] += d;
+          q4[j & 3] = fmaf(d, d, q4[j & 3]);
+        }
+        sd += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        sq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
       }
       tmem_st32(taddr + c * 32, v);  // parked for pass 2
 #pragma unroll
