@@ -274,6 +274,11 @@ def algorithmic_flops(name, args, latent_points=25, head_dim=64):
             return 4.0 * M * block * head_dim * heads
         # global attention: every token attends to its object's tokens (sum of squared segment lengths, set by main())
         return 4.0 * (SEG_SQ or n_seg * max_len * max_len) * head_dim * heads
+    if name == "pfpp_gemm_res_ln":  # h += A W^T: M x 512 x K (the LayerNorm is not counted)
+        return 2.0 * args[6] * 512 * args[7]
+    if name == "pfpp_attention_local":
+        M, heads, block = args[1], args[4], args[5]
+        return 4.0 * M * block * head_dim * heads
     if name == "pfpp_attention_varlen":
         n_seg, max_len, heads, hd = args[7], args[8], args[9], args[10]
         sq = n_seg * max_len * max_len if max_len <= latent_points else (SEG_SQ or n_seg * max_len * max_len)
@@ -292,7 +297,7 @@ class KernelProbe:
     NAMES = ("pfpp_gemm_bf16", "pfpp_gemm_bf16x3", "pfpp_gemm_f32", "pfpp_sa_fused", "pfpp_attention_tc",
              "pfpp_attention_varlen", "pfpp_rotate_fps", "pfpp_fps", "pfpp_ball_query", "pfpp_layernorm", "pfpp_vq",
              "pfpp_group_gather", "pfpp_group_max", "pfpp_embed_features", "pfpp_combine_embed", "pfpp_mean_pool",
-             "pfpp_ddpm_step")
+             "pfpp_ddpm_step", "pfpp_gemm_res_ln", "pfpp_attention_local")
 
     def __init__(self, lib):
         self.lib = lib
@@ -315,6 +320,8 @@ class KernelProbe:
                     key = f"{name}[level {args[0]}]"
                 elif name in ("pfpp_gemm_bf16", "pfpp_gemm_bf16x3"):
                     key = f"{name}[N={args[11]},K={args[12]}]"
+                elif name == "pfpp_gemm_res_ln":
+                    key = f"{name}[K={args[7]}]"
                 elif name == "pfpp_attention_tc":
                     key = f"{name}[{'local' if args[9] else 'global'}]"
                 r = probe.rec.setdefault(key, {"events": [], "flops": 0.0})

@@ -786,8 +786,9 @@ int launch_tc2_impl(const CUtensorMap& ma, const CUtensorMap& mb, const float* b
   cudaLaunchAttribute attr[1];
   if (MC) {
     const int items = ((tiles_m + 1) / 2) * tiles_n;
-    int grid = 2 * items < sm_count() ? 2 * items : (sm_count() & ~1);
-    cfg.gridDim = dim3(grid);
+    int pairs = items < sm_count() / 2 ? items : sm_count() / 2;
+    pairs = pfpp_cdiv(items, pfpp_cdiv(items, pairs));  // no more pairs than the round count needs
+    cfg.gridDim = dim3(2 * pairs);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
@@ -796,7 +797,9 @@ int launch_tc2_impl(const CUtensorMap& ma, const CUtensorMap& mb, const float* b
     cfg.numAttrs = 1;
   } else {
     const int tiles = tiles_n * tiles_m;
-    cfg.gridDim = dim3(tiles < sm_count() ? tiles : sm_count());
+    int ctas = tiles < sm_count() ? tiles : sm_count();
+    ctas = pfpp_cdiv(tiles, pfpp_cdiv(tiles, ctas));
+    cfg.gridDim = dim3(ctas);
   }
   static const int nostore = getenv("PFPP_GEMM_DEBUG_NOSTORE") ? 1 : 0;  // ablation knob (results are not written)
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, bias, residual, ldr, C, ldc, M, N, K, nostore ? 0 : M);
@@ -844,7 +847,13 @@ int launch_tc3_impl(const GemmMaps& m, const float* bias, const float* residual,
   cfg.blockDim = dim3(T2_THREADS);
   cfg.dynamicSmemBytes = T3_SMEM_BYTES;
   cfg.stream = stream;
-  cfg.gridDim = dim3(2 * items < sm_count() ? 2 * items : (sm_count() & ~1));
+  // persistent CTA pairs: every pair runs ceil(items / pairs) tiles, so only as many pairs as that round count needs are
+  // launched (228 tiles on 74 pairs = 4 rounds = 57 pairs): same latency, and the SMs that would idle through the last
+  // round stay free for the kernels of the other streams
+  const int max_pairs = sm_count() / 2;
+  int pairs = items < max_pairs ? items : max_pairs;
+  pairs = pfpp_cdiv(items, pfpp_cdiv(items, pairs));
+  cfg.gridDim = dim3(2 * pairs);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;

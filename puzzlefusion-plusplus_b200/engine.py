@@ -166,8 +166,9 @@ class Engine:
         fused = self.bf16 and self.fused_sa
         chunks = 1 if fused else -(-F // min(self.chunk, max(F, 1)))
         enc = chunks * (3 * (3 if fused else 7) + 1) + 1
-        tc_local = self.bf16 and self.tc_attention
-        den = 4 + int(tc_local) + len(self.den.layers) * 11 + 6
+        tc_local = self.bf16 and self.tc_attention and self.local_tiles > 0  # tcgen05 local attention: + its segment table
+        fuse = self.bf16 and self.fused_ln and self.C == 512  # LayerNorms folded into the residual projections
+        den = 4 + int(tc_local) + len(self.den.layers) * (8 if fuse else 11) + int(fuse) + 6
         return 3 + enc + den
 
     # ------------------------------------------------------------------ helpers

@@ -47,7 +47,7 @@ for level, N, S, NS, D, C1, C2, C3 in LEVELS:
     us = float(np.median(ts))
     flops = 2.0 * K * S * NS * ((3 + D) * C1 + C1 * C2 + C2 * C3)
     print(f"level {level}: {us:8.1f} us   {flops / us / 1e6:7.1f} TFLOP/s   checksum {out.float().sum().item():.4e}")
-    if "--trace" in sys.argv:
+    if "--trace" in sys.argv and level > 1:
         rows_per_cta = 128 if level == 1 else 256
         grid = (K * S * NS + rows_per_cta - 1) // rows_per_cta
         tr = torch.zeros(grid, 16, dtype=torch.int64, device=dev)  # persistent CTAs stamp their first tile only
