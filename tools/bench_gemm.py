@@ -8,8 +8,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from puzzlefusion_plusplus_b200 import _lib  # noqa: E402
 
-SHAPES = [("qkv", 16000, 1536, 512, 0, 1, 0), ("outproj", 16000, 512, 512, 0, 0, 1), ("ff1_geglu", 16000, 4096, 512, 4, 1, 0),
-          ("ff2", 16000, 512, 2048, 0, 0, 1), ("shape_emb", 16000, 512, 152, 0, 0, 0)]
+MS = [int(v) for v in sys.argv[1:]] or [16000]
+SHAPES = [s for M in MS for s in (("qkv", M, 1536, 512, 0, 1, 0), ("outproj", M, 512, 512, 0, 0, 1), ("ff1_geglu", M, 4096, 512, 4, 1, 0),
+                                  ("ff2", M, 512, 2048, 0, 0, 1), ("shape_emb", M, 512, 152, 0, 0, 0))]
 
 
 def main():
