@@ -587,22 +587,32 @@ __global__ void __launch_bounds__(128 * NWG, 1)
       acc_phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < COUT / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + c * 32, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      auto epi_chunk = [&](const uint32_t* v, int c) {
         uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float a = fmaxf(__uint_as_float(v[j]) + bias[c * 32 + j], 0.f);
-          float b = fmaxf(__uint_as_float(v[j + 1]) + bias[c * 32 + j + 1], 0.f);
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
-          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + j);
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j]) + b4.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b4.y, 0.f));
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j + 2]) + b4.z, 0.f), fmaxf(__uint_as_float(v[j + 3]) + b4.w, 0.f));
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&p0);
+          pk[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           *reinterpret_cast<uint4*>(xbuf + xoff(row, c * 32 + i * 8)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      };
+      {  // the TMEM load of chunk c + 1 is in flight while chunk c is converted
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_addr, va);
+#pragma unroll 1
+        for (int c = 0; c < COUT / 32; c += 2) {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tmem_ld32(lane_addr + (c + 1) * 32, vb);
+          epi_chunk(va, c);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c + 2 < COUT / 32) tmem_ld32(lane_addr + (c + 2) * 32, va);
+          epi_chunk(vb, c + 1);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -630,19 +640,31 @@ __global__ void __launch_bounds__(128 * NWG, 1)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int ch = mb * 128 + wq * 32 + lane;
         const float bias = b2s[ch];
-#pragma unroll 1
-        for (int g = 0; g < Cfg::GS; ++g) {
+        {  // max over each group's NS rows = TMEM columns; the load of chunk q + 1 is in flight while chunk q is reduced
+          constexpr int CPG = NS / 32;  // 32-column chunks per group; the tile has 128 columns = 4 chunks
+          uint32_t va[32], vb[32];
           float m = -INFINITY;
+          auto reduce = [&](const uint32_t* v, int q) {
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int c = 0; c < NS / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(lane_addr + g * NS + c * 32, v);
+            for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+            m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+            if ((q + 1) % CPG == 0) {  // last chunk of group q / CPG
+              const long long grp = g0 + q / CPG;
+              if (grp < p.groups) p.out[grp * C3 + ch] = __float2bfloat16_rn(fmaxf(m + bias, 0.f));
+              m = -INFINITY;
+            }
+          };
+          tmem_ld32(lane_addr, va);
+#pragma unroll
+          for (int q = 0; q < 4; q += 2) {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+            tmem_ld32(lane_addr + (q + 1) * 32, vb);
+            reduce(va, q);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (q + 2 < 4) tmem_ld32(lane_addr + (q + 2) * 32, va);
+            reduce(vb, q + 1);
           }
-          const long long grp = g0 + g;
-          if (grp < p.groups) p.out[grp * C3 + ch] = __float2bfloat16_rn(fmaxf(m + bias, 0.f));
         }
         // the next channel block / tile reuses the same TMEM columns: the whole group must have drained them
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
