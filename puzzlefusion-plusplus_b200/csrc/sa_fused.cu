@@ -310,13 +310,15 @@ __global__ void __launch_bounds__(128 * SUB + 32, SaCfg<NS, D, C1, C2, C3, STAGE
     // epilogue: thread = row; (+ xyz terms) + bias + ReLU -> bf16 -> next operand tile (in place).  The TMEM load of
     // chunk c + 1 is in flight while chunk c is converted (two register buffers, ping-pong).
     const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16) + sub * Cfg::CW;
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     auto epi_chunk = [&](const uint32_t* v, int c) {
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + j);
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j]) + b4.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b4.y, 0.f));
-        __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j + 2]) + b4.z, 0.f), fmaxf(__uint_as_float(v[j + 3]) + b4.w, 0.f));
+        // ReLU on the packed pair after rounding (== rounding after ReLU: monotone, 0 is exact): one HMNMX2 for two values
+        __nv_bfloat162 p0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y), zero2);
+        __nv_bfloat162 p1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w), zero2);
         pk[j >> 1] = *reinterpret_cast<uint32_t*>(&p0);
         pk[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
       }
@@ -587,13 +589,15 @@ __global__ void __launch_bounds__(128 * NWG, 1)
       acc_phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
       auto epi_chunk = [&](const uint32_t* v, int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + j);
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j]) + b4.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b4.y, 0.f));
-          __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[j + 2]) + b4.z, 0.f), fmaxf(__uint_as_float(v[j + 3]) + b4.w, 0.f));
+          // ReLU on the packed pair after rounding (== rounding after ReLU: monotone, 0 is exact): one HMNMX2 for two values
+          __nv_bfloat162 p0 = __hmax2(__floats2bfloat162_rn(__uint_as_float(v[j]) + b4.x, __uint_as_float(v[j + 1]) + b4.y), zero2);
+          __nv_bfloat162 p1 = __hmax2(__floats2bfloat162_rn(__uint_as_float(v[j + 2]) + b4.z, __uint_as_float(v[j + 3]) + b4.w), zero2);
           pk[j >> 1] = *reinterpret_cast<uint32_t*>(&p0);
           pk[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
         }
