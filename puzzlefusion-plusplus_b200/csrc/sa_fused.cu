@@ -207,6 +207,27 @@ __global__ void __launch_bounds__(128 * SUB + 32, SaCfg<NS, D, C1, C2, C3, STAGE
   uint32_t acc_par = 0;  // phase parity of bar_acc at the start of the tile (flips per tile when ACC_USES is odd)
   const float* cst = reinterpret_cast<const float*>(bp + Cfg::OFF_CONST);
 
+  // Row geometry of the NEXT tile is fetched while the current tile computes: the neighbour index at the top of a tile,
+  // the two dependent loads (the neighbour's xyz, the group's centroid) before the layer-1 accumulator wait -- the
+  // gather phase of a tile then starts with its source rows in registers and their coordinates in L1 (two L2 round
+  // trips less).
+  int nx_idx = -1, nx_off = -1;
+  auto fetch_idx = [&](long long t) {  // stage A: neighbour index of this thread's row in tile t
+    const long long g = t * Cfg::G + threadIdx.x / NS;
+    nx_idx = (t < n_tiles && g < p.groups) ? p.gidx[g * NS + (threadIdx.x % NS)] : -1;
+  };
+  auto fetch_xyz = [&](long long t) {  // stage B: source row; its coordinates and the centroid are pulled into L1
+    nx_off = -1;
+    if (nx_idx >= 0) {
+      const long long g = t * Cfg::G + threadIdx.x / NS;
+      nx_off = (int)(g / p.S) * p.N + nx_idx;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.xyz + (long long)nx_off * 3));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.new_xyz + g * 3));
+    }
+  };
+  fetch_idx(blockIdx.x);
+  fetch_xyz(blockIdx.x);
+
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
   const long long g0 = tile * Cfg::G;
   const bool tr0 = tile == blockIdx.x;  // trace stamps: first tile only
@@ -225,17 +246,14 @@ __global__ void __launch_bounds__(128 * SUB + 32, SaCfg<NS, D, C1, C2, C3, STAGE
     int* src_row = reinterpret_cast<int*>(bp + Cfg::OFF_ROWS);  // source point index in [0, K*N), -1 = padding
     {
       const int r = threadIdx.x;  // 0 .. ROWS-1
-      const long long g = g0 + r / NS;
-      const bool valid = g < p.groups;
-      int off = -1;
+      const int off = nx_off;     // -1 = padding row
       float d[3] = {0.f, 0.f, 0.f}, hi[3], lo[3];  // this row: xyz[idx] - centroid (fp32), then its bf16 hi/lo split
-      if (valid) {
-        const int idx = p.gidx[g * NS + (r % NS)];
-        off = (int)(g / p.S) * p.N + idx;
+      if (off >= 0) {
         const float* px = p.xyz + (long long)off * 3;
-        const float* pc = p.new_xyz + g * 3;
+        const float* pc = p.new_xyz + (g0 + r / NS) * 3;
         d[0] = fsub(px[0], pc[0]), d[1] = fsub(px[1], pc[1]), d[2] = fsub(px[2], pc[2]);
       }
+      fetch_idx(tile + gridDim.x);  // stage A for the next tile (consumed by fetch_xyz below)
       src_row[r] = off;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -302,6 +320,7 @@ __global__ void __launch_bounds__(128 * SUB + 32, SaCfg<NS, D, C1, C2, C3, STAGE
       }
       umma_commit(bar_acc);
     }
+    if (layer == 1) fetch_xyz(tile + gridDim.x);  // stage B for the next tile, under the layer-1 MMAs
     __syncwarp();
     mbar_wait(bar_acc, acc_phase ^ acc_par);
     acc_phase ^= 1;
@@ -522,22 +541,38 @@ __global__ void __launch_bounds__(128 * NWG, 1)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
 
-  for (long long tile = (long long)blockIdx.x * NWG + wg; tile < n_tiles; tile += (long long)gridDim.x * NWG) {
+  // row geometry of the group's NEXT tile is fetched under the current tile (see sa_fused_kernel)
+  int nx_idx = -1, nx_off = -1;
+  const long long tile_step = (long long)gridDim.x * NWG;
+  auto fetch_idx = [&](long long t) {
+    const long long g = t * Cfg::GS + t128 / NS;
+    nx_idx = (t < n_tiles && g < p.groups) ? p.gidx[g * NS + (t128 % NS)] : -1;
+  };
+  auto fetch_xyz = [&](long long t) {
+    nx_off = -1;
+    if (nx_idx >= 0) {
+      const long long g = t * Cfg::GS + t128 / NS;
+      nx_off = (int)(g / p.S) * p.N + nx_idx;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.xyz + (long long)nx_off * 3));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.new_xyz + g * 3));
+    }
+  };
+  fetch_idx((long long)blockIdx.x * NWG + wg);
+  fetch_xyz((long long)blockIdx.x * NWG + wg);
+
+  for (long long tile = (long long)blockIdx.x * NWG + wg; tile < n_tiles; tile += tile_step) {
     const long long g0 = tile * Cfg::GS;
     // ---------------- gather (thread = row): neighbour index, hi/lo offsets, then the feature rows by cp.async
     {
       const int r = t128;
-      const long long g = g0 + r / NS;
-      const bool valid = g < p.groups;
-      int off = -1;
+      const int off = nx_off;  // -1 = padding row
       float d[3] = {0.f, 0.f, 0.f}, hi[3], lo[3];
-      if (valid) {
-        const int idx = p.gidx[g * NS + (r % NS)];
-        off = (int)(g / p.S) * p.N + idx;
+      if (off >= 0) {
         const float* px = p.xyz + (long long)off * 3;
-        const float* pc = p.new_xyz + g * 3;
+        const float* pc = p.new_xyz + (g0 + r / NS) * 3;
         d[0] = fsub(px[0], pc[0]), d[1] = fsub(px[1], pc[1]), d[2] = fsub(px[2], pc[2]);
       }
+      fetch_idx(tile + tile_step);  // stage A for the next tile
       src_row[r] = off;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -584,6 +619,7 @@ __global__ void __launch_bounds__(128 * NWG, 1)
         if (layer == 0) umma_bf16(tmem, desc_kmajor_nosw(xyz_addr), desc_kmajor_nosw(base + Cfg::OFF_WXYZ), SF_IDESC, PANELS != 0);
         umma_commit(bar_acc);
       }
+      if (layer == 1) fetch_xyz(tile + tile_step);  // stage B for the next tile, under the layer-1 MMAs
       __syncwarp();
       mbar_wait(bar_acc, acc_phase);
       acc_phase ^= 1;
