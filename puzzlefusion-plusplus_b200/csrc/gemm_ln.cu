@@ -22,7 +22,8 @@
 //               accumulator + bias + residual -> shifted row sums -> value parked back in TMEM and written over the
 //               residual in its tile -> TMA store of h; (mean, M2) of the two column halves combined (Chan) through
 //               shared memory;
-//               pass 2, per 64-column slab: normalise + modulate -> bf16 -> swizzled box -> TMA store.
+//               pass 2, per 64-column slab: normalise + modulate (next TMEM load in flight) -> bf16 -> swizzled box in one
+//               of the warp's two dedicated tiles -> TMA store.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -140,8 +141,6 @@ __global__ void __launch_bounds__(GL_THREADS, 1)
       return t < 2 ? GL_OFF_EPI + (uint32_t)(ew * 2 + t) * 4096u : (uint32_t)(ew * (GL_RT - 2) + (t - 2)) * 4096u;
     };
     const uint32_t my_res = bar_res + 8 * (ew * GL_RT);
-    uint4* stage = reinterpret_cast<uint4*>(bp + tile_off(0));  // pass 2 re-uses tile 0 as its bf16 output box
-    const uint32_t stage_addr = base + tile_off(0);
     float* tab = reinterpret_cast<float*>(bp + GL_OFF_TAB);   // [0,512) bias, [512,1024) multiplier, [1024,1536) offset
     // the residual h[32 rows x 32 cols] of chunk c arrives by TMA, 128B-swizzled: the thread that owns a row reads it
     // with conflict-free 16-byte loads, overwrites it in place with the new h and the TMA engine stores the tile back --
@@ -236,49 +235,54 @@ __global__ void __launch_bounds__(GL_THREADS, 1)
     if (p.mod) mrow = row < p.M ? p.mod + (size_t)p.row_group[row / p.rows_per_group] * 2 * GL_C : mrow0;
     // the shared tables hold the first row's group: valid for this warp when all of its rows are in that group
     const bool uniform = __all_sync(0xffffffffu, mrow == mrow0);
+    // 32 columns of this thread's row -> 16 packed bf16 pairs
+    auto norm_chunk = [&](const uint32_t* v, int n, uint32_t* pk) {
+      if (uniform) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a4 = *reinterpret_cast<const float4*>(tab + GL_C + n + 4 * j);
+          const float4 b4 = *reinterpret_cast<const float4*>(tab + 2 * GL_C + n + 4 * j);
+          const float y0 = (__uint_as_float(v[4 * j]) - mean) * rstd * a4.x + b4.x;
+          const float y1 = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * a4.y + b4.y;
+          const float y2 = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * a4.z + b4.z;
+          const float y3 = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * a4.w + b4.w;
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
+          pk[2 * j] = *reinterpret_cast<uint32_t*>(&p0);
+          pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&p1);
+        }
+      } else {  // rows of different timesteps inside one warp (pfpp_denoiser_forward with mixed steps)
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float y0 = (__uint_as_float(v[j]) - mean) * rstd * (1.0f + mrow[n + j]) + mrow[GL_C + n + j];
+          const float y1 = (__uint_as_float(v[j + 1]) - mean) * rstd * (1.0f + mrow[n + j + 1]) + mrow[GL_C + n + j + 1];
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+      }
+    };
+    // the TMEM load of the next 32 columns is in flight while the current ones are normalised; the output boxes
+    // alternate between the warp's two dedicated tiles so that a slab only waits for the store two slabs back
+    uint32_t va[32], vb[32];
+    tmem_ld32(taddr, va);
 #pragma unroll 1
     for (int sl = 0; sl < 4; ++sl) {
       const int n0 = col0 + sl * 64;
       uint32_t pk[32];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[32];
-        tmem_ld32(taddr + sl * 64 + hh * 32, v);
-        const int n = n0 + hh * 32;
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (uniform) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 a4 = *reinterpret_cast<const float4*>(tab + GL_C + n + 4 * j);
-            const float4 b4 = *reinterpret_cast<const float4*>(tab + 2 * GL_C + n + 4 * j);
-            const float y0 = (__uint_as_float(v[4 * j]) - mean) * rstd * a4.x + b4.x;
-            const float y1 = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * a4.y + b4.y;
-            const float y2 = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * a4.z + b4.z;
-            const float y3 = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * a4.w + b4.w;
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
-            pk[hh * 16 + 2 * j] = *reinterpret_cast<uint32_t*>(&p0);
-            pk[hh * 16 + 2 * j + 1] = *reinterpret_cast<uint32_t*>(&p1);
-          }
-        } else {  // rows of different timesteps inside one warp (pfpp_denoiser_forward with mixed steps)
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float y0 = (__uint_as_float(v[j]) - mean) * rstd * (1.0f + mrow[n + j]) + mrow[GL_C + n + j];
-            const float y1 = (__uint_as_float(v[j + 1]) - mean) * rstd * (1.0f + mrow[n + j + 1]) + mrow[GL_C + n + j + 1];
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
-            pk[hh * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&b2);
-          }
-        }
-      }
-      // the previous box of this warp must have been read out of shared memory before it is overwritten
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tmem_ld32(taddr + sl * 64 + 32, vb);
+      norm_chunk(va, n0, pk);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (sl + 1 < 4) tmem_ld32(taddr + (sl + 1) * 64, va);
+      norm_chunk(vb, n0 + 32, pk + 16);
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the box of slab sl - 2 has been read
       __syncwarp();
-      uint4* srow = stage + lane * 8;
+      uint4* srow = reinterpret_cast<uint4*>(bp + tile_off(sl & 1)) + lane * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) srow[j ^ (lane & 7)] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0 && m0 + q * 32 < p.M) {
-        tma_store_2d(&map_o, stage_addr, n0, m0 + q * 32);
+      if (lane == 0) {
+        if (m0 + q * 32 < p.M) tma_store_2d(&map_o, base + tile_off(sl & 1), n0, m0 + q * 32);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
