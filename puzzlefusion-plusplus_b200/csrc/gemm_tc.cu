@@ -939,6 +939,9 @@ int gemm_dispatch(const void* A, const void* A_lo, int lda, const void* W, const
 
 }  // namespace
 
+int pfpp_gemm_small_x3(const void* A, int lda, const void* W, int ldw, const float* bias, void* C, int ldc, int c_split, int M,
+                       int N, int K, int epilogue, cudaStream_t stream);  // gemm_small.cu
+
 extern "C" int pfpp_has_tensor_core_path(void) { return 1; }
 
 extern "C" int pfpp_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, const float* residual,
@@ -960,6 +963,10 @@ extern "C" int pfpp_gemm_bf16x3(const void* A, int lda, const void* W, int ldw, 
   PFPP_CHECK_ARG((((uintptr_t)A) & 15) == 0 && (((uintptr_t)W) & 15) == 0);
   PFPP_CHECK_ARG(!c_split || (ldc % 2) == 0);
   if (M == 0) return PFPP_OK;
+  // a few hundred rows (the output heads: M = fragments): 32 x 64 tiles on warp-level MMAs instead of one or two
+  // 256 x 256 CTA-pair tiles whose fixed pipeline cost dominates (gemm_small.cu)
+  if (M <= 1024 && residual == nullptr && epilogue != PFPP_EPI_GEGLU)
+    return pfpp_gemm_small_x3(A, lda, W, ldw, bias, C, ldc, c_split, M, N, K, epilogue, stream);
   const __nv_bfloat16* a = (const __nv_bfloat16*)A;
   const __nv_bfloat16* w = (const __nv_bfloat16*)W;
   return gemm_dispatch(a, a + lda / 2, lda, w, w + ldw / 2, ldw, bias, residual, ldr, C, ldc, ldc / 2, c_split ? 2 : 0, M, N,

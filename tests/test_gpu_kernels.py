@@ -207,9 +207,10 @@ def _split(t, ld):
 @pytest.mark.parametrize("M,N,K,epi,c_split", [(300, 200, 136, 0, 0), (1000, 128, 64, 1, 1), (257, 512, 512, 2, 0),
                                                (8192, 64, 8, 1, 1), (500, 4096, 512, 4, 1), (640, 1536, 512, 0, 0),
                                                (100, 64, 512, 0, 0), (16000, 1536, 512, 0, 0), (6080, 2048, 256, 2, 1),
-                                               (16000, 512, 2048, 0, 0), (12345, 4096, 512, 4, 1), (4000, 520, 512, 2, 0)])
+                                               (16000, 512, 2048, 0, 0), (12345, 4096, 512, 4, 1), (4000, 520, 512, 2, 0),
+                                               (387, 1024, 512, 3, 1), (387, 3, 256, 0, 0), (13, 256, 512, 3, 1), (1024, 72, 24, 3, 0)])
 def test_gemm_bf16x3_fp32_grade(lib, M, N, K, epi, c_split):
-    """Split-operand tensor-core GEMM (3 tcgen05 passes over bf16 hi/lo halves): against the fp64 product of the
+    """Split-operand tensor-core GEMM (3 passes over bf16 hi/lo halves; tcgen05, or warp-level MMA for M <= 1024): against the fp64 product of the
     ORIGINAL fp32 operands the error must be fp32-grade -- 3e-5 of the result scale (2^-16 per product, ~100x below the
     plain bf16 GEMM), and a split output must reproduce the fp32 result to 2^-16 relative."""
     g = torch.Generator().manual_seed(M * 7 + N)
@@ -221,10 +222,13 @@ def test_gemm_bf16x3_fp32_grade(lib, M, N, K, epi, c_split):
         ref = torch.relu(ref)
     elif epi == 2:
         ref = torch.nn.functional.gelu(ref)
+    elif epi == 3:
+        ref = torch.nn.functional.silu(ref)
     elif epi == 4:
         ref = ref[:, 0::2] * torch.nn.functional.gelu(ref[:, 1::2])
     res = torch.randn(ref.shape, generator=g)
-    use_res = epi == 0 and not c_split
+    # M <= 1024 without a residual runs on the warp-MMA kernel of gemm_small.cu (the output heads), everything else on tcgen05
+    use_res = epi == 0 and not c_split and M > 1024
     if use_res:
         ref = ref + res.double()
     No = ref.shape[1]
