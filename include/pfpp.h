@@ -124,7 +124,9 @@ int pfpp_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* 
  * (relative error ~2^-16 per product; the reference's fp32 nn.Linear / conv1x1, same call sites as pfpp_gemm_f32).
  * A [M, lda >= 2K], W [N, ldw >= 2K] split; K multiple of 8, lda / ldw multiples of 16.  C is fp32 [M, ldc]
  * (c_split = 0; residual fp32, may alias C) or split [M, ldc] (c_split = 1: the operand of the next layer).
- * GELU / GEGLU epilogues use the exact erf form. */
+ * GELU / GEGLU epilogues use the exact erf form.  M <= 1024 without a residual (the output heads, M = fragments) runs the
+ * same three products as 32 x 64 tiles on warp-level MMAs (csrc/gemm_small.cu): a 256 x 256 tcgen05 tile pair is mostly
+ * fixed pipeline cost at that size. */
 int pfpp_gemm_bf16x3(const void* A, int lda, const void* W, int ldw, const float* bias, const float* residual, int ldr,
                      void* C, int ldc, int c_split, int M, int N, int K, int epilogue, cudaStream_t stream);
 
