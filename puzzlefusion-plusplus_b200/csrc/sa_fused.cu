@@ -227,6 +227,32 @@ __global__ void __launch_bounds__(128 * SUB + 32, SaCfg<NS, D, C1, C2, C3, STAGE
   };
   fetch_idx(blockIdx.x);
   fetch_xyz(blockIdx.x);
+  // Feature gather of a tile: every thread publishes its source row, then all threads stream the rows as 16-byte
+  // cp.async chunks (consecutive threads = consecutive chunks of a row) straight into the swizzled operand tile, every
+  // chunk in flight at once.  With EARLY_GATHER it is ISSUED one tile ahead -- for the first tile here, for every later tile as soon as
+  // the last layer-2 MMA block of the previous tile has completed (the operand buffer is free from then on) -- so its
+  // latency runs under that tile's last max-epilogue instead of in front of the layer-0 MMAs.
+  int* src_row = reinterpret_cast<int*>(bp + Cfg::OFF_ROWS);  // source point index in [0, K*N), -1 = padding
+  auto issue_gather = [&]() {
+    src_row[threadIdx.x] = nx_off;
+    SA_BAR();
+    constexpr int CPR = (D > 0 ? D : 8) / 8;   // 16-byte chunks per row
+    constexpr int TOTAL = Cfg::ROWS * CPR;
+#pragma unroll 1
+    for (int ch = threadIdx.x; ch < TOTAL; ch += Cfg::ROWS) {
+      const int r = ch / CPR, c8 = ch % CPR;
+      const int off = src_row[r];
+      const uint32_t dst = base + Cfg::OFF_X + (r >> 7) * Cfg::X_BYTES + xoff(r & 127, c8 * 8);
+      const void* src = off >= 0 ? (const void*)(p.feats + (long long)off * D + c8 * 8) : (const void*)p.feats;
+      const int nbytes = off >= 0 ? 16 : 0;  // padding rows: zero fill
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // (level 3 runs one CTA per SM: nothing shares the SM during the early issue, and measured it is slower there --
+  // 374 vs 353 us -- so the early issue is used only when CTAs share an SM: level 2, 436 -> 415 us)
+  constexpr bool EARLY_GATHER = D > 0 && Cfg::MINB >= 2;
+  if (EARLY_GATHER && (long long)blockIdx.x < n_tiles) issue_gather();
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
   const long long g0 = tile * Cfg::G;
@@ -238,50 +264,29 @@ __global__ void __launch_bounds__(128 * SUB + 32, SaCfg<NS, D, C1, C2, C3, STAGE
   int row = wq * 32 + lane;                                            // row inside this thread's sub-tile
   asm volatile("" : "+r"(row));
   uint8_t* xsub = bp + Cfg::OFF_X + sub * Cfg::X_BYTES;                // this sub-tile's operand buffer
-  // ---------------- gather: X0[row] = feats[idx] (bf16, swizzled) ----------
-  // phase 1: thread = row -> neighbour index, xyz offset; phase 2: all threads stream the feature rows as
-  // 16-byte cp.async chunks (consecutive threads = consecutive chunks of a row) straight into the swizzled
-  // operand tile, every chunk of the tile in flight at once.
+  // ---------------- operands of layer 0: the (dx,dy,dz) hi/lo rows now, the feature rows issued one tile ahead ----------
   {
-    int* src_row = reinterpret_cast<int*>(bp + Cfg::OFF_ROWS);  // source point index in [0, K*N), -1 = padding
-    {
-      const int r = threadIdx.x;  // 0 .. ROWS-1
-      const int off = nx_off;     // -1 = padding row
-      float d[3] = {0.f, 0.f, 0.f}, hi[3], lo[3];  // this row: xyz[idx] - centroid (fp32), then its bf16 hi/lo split
-      if (off >= 0) {
-        const float* px = p.xyz + (long long)off * 3;
-        const float* pc = p.new_xyz + (g0 + r / NS) * 3;
-        d[0] = fsub(px[0], pc[0]), d[1] = fsub(px[1], pc[1]), d[2] = fsub(px[2], pc[2]);
-      }
-      fetch_idx(tile + gridDim.x);  // stage A for the next tile (consumed by fetch_xyz below)
-      src_row[r] = off;
+    const int r = threadIdx.x;  // 0 .. ROWS-1
+    const int off = nx_off;     // -1 = padding row
+    float d[3] = {0.f, 0.f, 0.f}, hi[3], lo[3];  // this row: xyz[idx] - centroid (fp32), then its bf16 hi/lo split
+    if (off >= 0) {
+      const float* px = p.xyz + (long long)off * 3;
+      const float* pc = p.new_xyz + (g0 + r / NS) * 3;
+      d[0] = fsub(px[0], pc[0]), d[1] = fsub(px[1], pc[1]), d[2] = fsub(px[2], pc[2]);
+    }
+    fetch_idx(tile + gridDim.x);  // stage A for the next tile (consumed by fetch_xyz below)
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        hi[i] = __bfloat162float(__float2bfloat16_rn(d[i]));
-        lo[i] = d[i] - hi[i];
-      }
-      // k = [x_hi y_hi z_hi | x_lo y_lo z_lo | x_hi y_hi z_hi | 0 ...] against the weight row built above
-      uint8_t* xb = bp + Cfg::OFF_XYZ + (r >> 7) * 4096;
-      *reinterpret_cast<uint4*>(xb + xyzoff(r & 127, 0)) =
-          make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], lo[0]), pack_bf16(lo[1], lo[2]), pack_bf16(hi[0], hi[1]));
-      *reinterpret_cast<uint4*>(xb + xyzoff(r & 127, 1)) = make_uint4(pack_bf16(hi[2], 0.f), 0u, 0u, 0u);
+    for (int i = 0; i < 3; ++i) {
+      hi[i] = __bfloat162float(__float2bfloat16_rn(d[i]));
+      lo[i] = d[i] - hi[i];
     }
-    if (D > 0) {
-      SA_BAR();
-      constexpr int CPR = D / 8;                 // 16-byte chunks per row
-      constexpr int TOTAL = Cfg::ROWS * CPR;
-#pragma unroll 1
-      for (int ch = threadIdx.x; ch < TOTAL; ch += Cfg::ROWS) {
-        const int r = ch / CPR, c8 = ch % CPR;
-        const int off = src_row[r];
-        const uint32_t dst = base + Cfg::OFF_X + (r >> 7) * Cfg::X_BYTES + xoff(r & 127, c8 * 8);
-        const void* src = off >= 0 ? (const void*)(p.feats + (long long)off * D + c8 * 8) : (const void*)p.feats;
-        const int nbytes = off >= 0 ? 16 : 0;  // padding rows: zero fill
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+    // k = [x_hi y_hi z_hi | x_lo y_lo z_lo | x_hi y_hi z_hi | 0 ...] against the weight row built above
+    uint8_t* xb = bp + Cfg::OFF_XYZ + (r >> 7) * 4096;
+    *reinterpret_cast<uint4*>(xb + xyzoff(r & 127, 0)) =
+        make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], lo[0]), pack_bf16(lo[1], lo[2]), pack_bf16(hi[0], hi[1]));
+    *reinterpret_cast<uint4*>(xb + xyzoff(r & 127, 1)) = make_uint4(pack_bf16(hi[2], 0.f), 0u, 0u, 0u);
+    if (D > 0 && !EARLY_GATHER) issue_gather();
+    if (D > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");  // this tile's feature rows have landed
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -392,6 +397,8 @@ __global__ void __launch_bounds__(128 * SUB + 32, SaCfg<NS, D, C1, C2, C3, STAGE
       acc_phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tr0 && mb < 4) SA_TRACE(6 + 2 * mb);
+      // every MMA of this tile has completed: the operand buffer is free -> start the next tile's feature gather
+      if (EARLY_GATHER && mb == Cfg::MB3 - 1 && tile + gridDim.x < n_tiles) issue_gather();
       const int ch = mb * 128 + wq * 32 + lane;
       const float bias = b2s[ch];
       {  // max over each group's NS rows = TMEM columns; the load of chunk q + 1 is in flight while chunk q is reduced
