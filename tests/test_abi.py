@@ -114,7 +114,17 @@ def test_argument_errors_are_negative_codes_without_touching_the_gpu():
     assert lib.pfpp_attention_tc(one, 1000, 1536, 512, one, one, 1, 500, 7, 0, one, 512, null) < 0   # C != heads*64
     assert lib.pfpp_layernorm(one, null, null, null, null, null, 0, 10, 384, 0, one, null, null) < 0  # C not 256/512
     assert lib.pfpp_sa_fused(4, one, one, one, one, 1, 8, 4, one, one, one, one, one, one, one, one, null) < 0  # level
+    # the fused residual projection + LayerNorm and the warp-MMA local attention
+    assert lib.pfpp_gemm_res_ln(null, 512, one, 512, null, one, 128, 512, null, null, 0, one, one, one, null) < 0   # A NULL
+    assert lib.pfpp_gemm_res_ln(one, 512, one, 512, null, one, 128, 512, null, null, 0, null, null, one, null) < 0  # no LN params
+    assert lib.pfpp_gemm_res_ln(one, 512, one, 512, null, one, 128, 508, null, null, 0, one, one, one, null) < 0   # K % 8 != 0
+    assert lib.pfpp_gemm_res_ln(one, 512, one, 512, null, one, 128, 512, one, null, 25, null, null, one, null) < 0  # AdaLN without groups
+    assert lib.pfpp_attention_local(one, 100, 1536, 512, 8, 33, one, 512, null) < 0    # block > 32
+    assert lib.pfpp_attention_local(one, 101, 1536, 512, 8, 25, one, 512, null) < 0    # M not a multiple of the block
+    assert lib.pfpp_attention_local(one, 100, 1536, 512, 7, 25, one, 512, null) < 0    # C != heads * 64
     # empty problems are fine and launch nothing
+    assert lib.pfpp_gemm_res_ln(one, 512, one, 512, null, one, 0, 512, null, null, 0, one, one, one, null) == 0
+    assert lib.pfpp_attention_local(one, 0, 1536, 512, 8, 25, one, 512, null) == 0
     assert lib.pfpp_fps(one, 0, 8, 4, null, one, null, null) == 0
     assert lib.pfpp_ball_query(one, one, 0, 8, 4, f(0.04), 32, one, null) == 0
     assert lib.pfpp_gemm_bf16(one, 8, one, 8, null, null, 0, one, 8, 0, 0, 8, 8, 0, null) == 0
