@@ -161,11 +161,15 @@ class Engine:
         self.cw_den.tc_attention, self.cw_den.local_tiles = int(self.tc_attention), self.local_tiles
         self.cw_den.fused_ln = int(self.fused_ln)
 
-    def step_kernels(self, F):
-        """kernels one DDPM step launches (bench.py's gpu_launches; the coarse entry points launch whole sequences)"""
+    def step_kernels(self, F, n_enc=None):
+        """kernels one DDPM step launches (bench.py's gpu_launches; the coarse entry points launch whole sequences).
+        n_enc: fragments re-encoded per step when the reference parts' rows are cached (None: all F, no scatter)."""
         fused = self.bf16 and self.fused_sa
-        chunks = 1 if fused else -(-F // min(self.chunk, max(F, 1)))
-        enc = chunks * (3 * (3 if fused else 7) + 1) + 1
+        Fe = F if n_enc is None else n_enc
+        chunks = 1 if fused else -(-Fe // min(self.chunk, max(Fe, 1)))
+        enc = chunks * (3 * (3 if fused else 7) + 1) + 1 + (0 if n_enc is None else 2)  # + the two row scatters
+        if Fe == 0:
+            enc = 0
         tc_local = self.bf16 and self.tc_attention and self.local_tiles > 0  # tcgen05 local attention: + its segment table
         fuse = self.bf16 and self.fused_ln and self.C == 512  # LayerNorms folded into the residual projections
         den = 4 + int(tc_local) + len(self.den.layers) * (8 if fuse else 11) + int(fuse) + 6
@@ -527,7 +531,7 @@ class Engine:
              step_ctr.data_ptr(), noise_all.data_ptr(), noise_all.stride(0), hist.data_ptr(), hist.stride(0),
              seg_local[0].data_ptr(), seg_local[1].data_ptr(), seg_global[0].data_ptr(), seg_global[1].data_ptr(), F,
              seg_global[0].numel(), max_global, N, _lib.ptr(enc_slot), _lib.ptr(enc_pos), n_enc, latent.data_ptr(),
-             xyz.data_ptr(), None, ws.data_ptr(), n, kernels=self.step_kernels(F))
+             xyz.data_ptr(), None, ws.data_ptr(), n, kernels=self.step_kernels(F, None if enc_slot is None else n_enc))
 
     # ------------------------------------------------------------------ verifier
     def verifier_logits(self, feat, tok_row, tok_i, tok_j, seg_start, seg_len, max_len, n_rows):
